@@ -1,0 +1,113 @@
+"""Host-side rate-constant preparation (inputs of the hot path, not part of it).
+
+The reference evaluates rate expressions with ``kmos.evaluate_rate_expression``
+(kmos/__init__.py:67-189): tokenise, substitute unit constants (kmos/units.py), ``m_<formula>``
+masses (ASE), ``mu_<gas>`` chemical potentials (JANAF tables, downloaded from NIST by
+kmos/species.py:47-96) and the model parameters, then ``eval``.  The GPU box has neither kmos, ASE
+nor network, so this module restates just enough of that to turn the rate expressions stored in the
+model fixtures into the ``rates[R][P]`` matrix that both the oracle and the CUDA engine consume.
+Because both sides are fed the same numbers, parity does not depend on this file.
+
+``standin_mu`` replaces the JANAF interpolation by a closed form (documented stand-in).
+"""
+import math
+import re
+import tokenize
+from io import StringIO
+
+# CODATA 2010 values as in kmos/units.py:26-36
+UNITS = {
+    "pi": 3.14159265358979323846,
+    "c": 2.99792458e8,
+    "h": 6.62606957e-34,
+    "hbar": 1.054571726e-34,
+    "eV": 1.602176565e-19,
+    "kboltzmann": 1.3806488e-23,
+    "umass": 1.660538921e-27,
+    "angstrom": 1.0e-10,
+    "bar": 1.0e5,
+}
+UNIT_KEYS = ["pi", "c", "h", "hbar", "eV", "kboltzmann", "umass", "angstrom", "bar"]
+
+# ASE >= 3.13 (IUPAC 2016) atomic masses for the elements the example models use
+ATOMIC_MASSES = {"H": 1.008, "C": 12.011, "N": 14.007, "O": 15.999}
+ATOMIC_MASSES_LEGACY = {"H": 1.00794, "C": 12.0107, "N": 14.0067, "O": 15.9994}
+
+RATE_ALIASES = {"beta": "(1/(kboltzmann*T))"}
+
+_KB_EV = 8.6173324e-5
+
+# mu0(T) ~ a + b*T*(1 - ln(T/298.15)) eV at 1 bar: crude ideal-gas-like shape, NOT JANAF.
+_MU_STANDIN = {
+    "COgas": (-0.0, -2.05e-3),
+    "O2gas": (-0.0, -2.13e-3),
+    "CO2gas": (-0.0, -2.22e-3),
+    "H2gas": (-0.0, -1.35e-3),
+}
+
+
+def standin_mu(name, T, p):
+    """Chemical potential stand-in in eV: linear-in-T entropy term + k_B T ln p (T in K, p in bar)."""
+    key = name if name in _MU_STANDIN else name + "gas"
+    a, b = _MU_STANDIN.get(key, (0.0, -2.0e-3))
+    T = float(T)
+    return a + b * (T - 298.15) * 0.5 + b * T * 0.5 * math.log(max(T, 1.0) / 298.15) \
+        + _KB_EV * T * math.log(float(p))
+
+
+def _string2symbols(s):
+    out = []
+    for sym, count in re.findall(r"([A-Z][a-z]?)(\d*)", s):
+        out.extend([sym] * (int(count) if count else 1))
+    return out
+
+
+def evaluate_rate_expression(rate_expr, parameters=None, mu=standin_mu, masses=ATOMIC_MASSES):
+    """Mirror of kmos.evaluate_rate_expression (kmos/__init__.py:67-189).
+
+    ``parameters``: {name: {"value": v}} or {name: v}.  Same textual substitution + eval so that the
+    floating-point result is the one the reference computes given the same masses and mu.
+    """
+    parameters = parameters or {}
+    pdict = {}
+    for k, v in parameters.items():
+        pdict[k] = v["value"] if isinstance(v, dict) else v
+    if not rate_expr:
+        return 0.0
+    for old, new in RATE_ALIASES.items():
+        rate_expr = rate_expr.replace(old, new)
+    tokens = list(tokenize.generate_tokens(StringIO(rate_expr).readline))
+    replaced = []
+    for i, token, _, _, _ in tokens:
+        if token in ["sqrt", "exp", "sin", "cos", "pi", "pow", "log"]:
+            replaced.append((i, "math." + token))
+        elif token in UNITS:
+            replaced.append((i, str(UNITS[token])))
+        elif token.startswith("m_"):
+            species_name = "_".join(token.split("_")[1:])
+            replaced.append((i, "%s" % sum(masses[s] for s in _string2symbols(species_name))))
+        elif token.startswith("mu_"):
+            species_name = "_".join(token.split("_")[1:])
+            replaced.append((i, repr(mu(species_name, pdict["T"], pdict["p_%s" % species_name]))))
+        elif token in pdict:
+            s = str(pdict[token])
+            for unit in UNIT_KEYS:
+                s = s.replace(unit, "%s" % UNITS[unit])
+            replaced.append((i, s))
+        else:
+            replaced.append((i, token))
+    expr = tokenize.untokenize(replaced)
+    return float(eval(expr, {"__builtins__": {}, "math": math}))
+
+
+def model_rates(ir, overrides=None, **kw):
+    """rates[P] for a model fixture: every process' rate_constant with parameter overrides applied."""
+    params = {k: dict(v) for k, v in ir["parameters"].items()}
+    for k, v in (overrides or {}).items():
+        params.setdefault(k, {})["value"] = v
+    by_name = {p["name"].lower(): p for p in ir["process_defs"]}
+    out = []
+    for name in ir["procs"]:
+        pd = by_name[name.lower()]
+        out.append(evaluate_rate_expression(pd["rate_constant"], params, **kw) if pd["enabled"] else 0.0)
+    return out

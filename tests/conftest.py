@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+def load_model(name, with_device=True):
+    """(ir, blob, info) of tests/golden/models/<name>.json"""
+    from kmos_b200 import tables
+    ir = tables.load_ir(os.path.join(GOLDEN, "models", name + ".json"))
+    blob, info = tables.build_blob(ir, with_device=with_device)
+    return ir, blob, info
