@@ -16,7 +16,7 @@ Sections
     SEC_INIT       n_layers x (defaults_routine, touchup_routine): initialize_state's two loop bodies
                    (proclist_generic_subroutines.mpy:261-299)
     SEC_GR         otf: n_gr x (routine, proc, nvars, lut_offset, radix[MAX_VARS])
-    SEC_PROCSITE   n_proc x site-type mask: bit (n-1) set if the process can be registered on site n
+    SEC_PROCSITE   n_proc x site type (1-based) the process is registered on (0: several -> unsupported)
     SEC_DEVICE     compiled per-event lane tables for the CUDA engine (kmos_b200.devtables)
 
 Coordinates are 4-vectors [dx,dy,dz,dn] added to the routine's base coordinate, exactly like the
@@ -25,14 +25,14 @@ Coordinates are 4-vectors [dx,dy,dz,dn] added to the routine's base coordinate, 
 import numpy as np
 
 MAGIC = 0x4B423230
-VERSION = 3
+VERSION = 4
 
 BACKENDS = {"local_smart": 0, "lat_int": 1, "otf": 2}
 
 SEC_ROUTINES, SEC_CODE, SEC_RUNPROC, SEC_INIT, SEC_GR, SEC_PROCSITE, SEC_DEVICE = range(1, 8)
 
 (OP_REPLACE, OP_IF_CAN, OP_DEL, OP_ADD, OP_DEL_NLI, OP_ADD_NLI, OP_ADD_RATE, OP_UPD_RATE, OP_SELECT,
- OP_CASE, OP_DEL_ALL, OP_CALL, OP_RETURN, OP_INC) = range(1, 15)
+ OP_CASE, OP_DEL_ALL, OP_CALL, OP_RETURN, OP_INC, OP_JUMP) = range(1, 16)
 
 MAX_VARS = 8
 CASE_DEFAULT = -1  # mask with every bit set
@@ -119,10 +119,16 @@ class _Assembler(object):
                         if s < 0:
                             raise TableError("case(null_species) not supported")
                         mask |= 1 << s
-                cases.append([OP_CASE, mask, len(b)] + b)
+                cases.append([mask, b])
             # `case default` is evaluated last, wherever it was written
-            cases.sort(key=lambda c: c[1] == CASE_DEFAULT)
-            flat = [w for c in cases for w in c]
+            cases.sort(key=lambda c: c[0] == CASE_DEFAULT)
+            # every case body ends in OP_JUMP <words to skip to the end of the select>, so that a
+            # non-recursive interpreter can fall out of the taken case (kmos_b200/csrc/kb_interp.h)
+            flat = []
+            remaining = sum(3 + len(b) + 2 for _m, b in cases)
+            for mask, b in cases:
+                remaining -= 3 + len(b) + 2
+                flat += [OP_CASE, mask, len(b) + 2] + b + [OP_JUMP, remaining]
             return [OP_SELECT] + st[1] + [len(cases), len(flat)] + flat
         if k == "del_all":
             return [OP_DEL_ALL] + st[1]
@@ -169,7 +175,7 @@ def proc_site_masks(ir):
 
     def walk(block, base_n):
         for st in block:
-            if st[0] in ("add", "del") and not isinstance(st[1], list):
+            if st[0] == "add" and not isinstance(st[1], list):  # registered only where it is added
                 masks[st[1] - 1] |= 1 << (base_n + st[2][3] - 1)
             elif st[0] == "if_can":
                 walk(st[3], base_n)
@@ -180,6 +186,15 @@ def proc_site_masks(ir):
         if name in rsite:
             walk(stmts, rsite[name])
     return masks
+
+
+def proc_anchor_types(ir):
+    """1-based site type each process is registered on; 0 if it is registered on several (unsupported by
+    the per-cell avail_sites layout of the engine)."""
+    out = []
+    for mask in proc_site_masks(ir):
+        out.append(mask.bit_length() if mask and not (mask & (mask - 1)) else 0)
+    return out
 
 
 def build_blob(ir, with_device=True):
@@ -242,7 +257,7 @@ def build_blob(ir, with_device=True):
         (SEC_RUNPROC, runproc),
         (SEC_INIT, init),
         (SEC_GR, gr_words),
-        (SEC_PROCSITE, proc_site_masks(ir)),
+        (SEC_PROCSITE, proc_anchor_types(ir)),
     ]
     info = {"routine_ids": dict(asm.routine_ids), "gr": gr_info, "lut_total": lut_total,
             "n_routines": len(asm.routine_code)}

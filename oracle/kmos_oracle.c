@@ -30,11 +30,11 @@
 #include <string.h>
 
 #define KB20_MAGIC 0x4B423230
-#define KB20_VERSION 3
+#define KB20_VERSION 4
 enum { SEC_ROUTINES = 1, SEC_CODE, SEC_RUNPROC, SEC_INIT, SEC_GR, SEC_PROCSITE, SEC_DEVICE };
 enum {
     OP_REPLACE = 1, OP_IF_CAN, OP_DEL, OP_ADD, OP_DEL_NLI, OP_ADD_NLI, OP_ADD_RATE, OP_UPD_RATE, OP_SELECT,
-    OP_CASE, OP_DEL_ALL, OP_CALL, OP_RETURN, OP_INC
+    OP_CASE, OP_DEL_ALL, OP_CALL, OP_RETURN, OP_INC, OP_JUMP
 };
 enum { BACKEND_LOCAL_SMART = 0, BACKEND_LAT_INT = 1, BACKEND_OTF = 2 };
 enum { ORACLE_RNG_PHILOX = 0, ORACLE_RNG_GFORTRAN = 1 };
@@ -430,6 +430,9 @@ static int exec_block(oracle_t *o, const int32_t *pc, const int32_t *end, const 
         case OP_INC:
             o->nr_vars[pc[1]]++;
             pc += 2;
+            break;
+        case OP_JUMP: /* end of a case body (flat interpreters skip the remaining cases here) */
+            pc = end;
             break;
         default:
             o->status = ORACLE_BAD_MODEL;
