@@ -1,0 +1,210 @@
+"""Batched front-end over the C-ABI: R replicas of one kmos model on one GPU.
+
+Mirrors, batched, what ``kmos.run.KMC_Model`` does with the f2py module (kmos/run/__init__.py:155-340,
+416-432, 680-850): set rate constants, initialise the lattice, ``do_steps(n)``, read kmc_time / procstat /
+integ_rates / occupation, derive TOFs.  All arrays carry a leading replica axis.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi, tables
+
+
+class Model(object):
+    """The rule tables of one exported kmos model (what ``kmos export`` would compile)."""
+
+    def __init__(self, ir=None, blob=None, info=None):
+        if blob is None:
+            blob, info = tables.build_blob(ir)
+        self.ir, self.blob, self.info = ir, np.ascontiguousarray(blob, dtype=np.int32), info
+        L = capi.lib()
+        h = C.c_void_p()
+        capi.check(L.kmos_b200_model_create(self.blob, self.blob.size, C.byref(h)))
+        self.h = h
+        self.n_proc = L.kmos_b200_model_nproc(h)
+        self.n_species = L.kmos_b200_model_nspecies(h)
+        self.spuck = L.kmos_b200_model_spuck(h)
+        self.lut_size = L.kmos_b200_model_lut_size(h)
+        self.backend = int(self.blob[2])
+        self.default_layer = int(self.blob[9])
+
+    @classmethod
+    def from_json(cls, path):
+        return cls(ir=tables.load_ir(path))
+
+    def close(self):
+        if getattr(self, "h", None):
+            capi.lib().kmos_b200_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch(object):
+    def __init__(self, model, n_replicas, size, device=0, seeds=None, replica_ids=None, rates=None, lut=None,
+                 kernel=capi.KERNEL_AUTO, init=True, layer=None):
+        self.L = capi.lib()
+        self.model = model
+        self.R = int(n_replicas)
+        size3 = np.ones(3, dtype=np.int32)
+        size = np.atleast_1d(np.asarray(size, dtype=np.int32))
+        size3[:len(size)] = size
+        self.size = size3
+        h = C.c_void_p()
+        capi.check(self.L.kmos_b200_batch_create(model.h, self.R, size3, int(device), C.byref(h)))
+        self.h = h
+        self.P = model.n_proc
+        self.volume = self.L.kmos_b200_batch_volume(h)
+        self.ncells = self.volume // model.spuck
+        self.layer = model.default_layer if layer is None else int(layer)
+        if kernel != capi.KERNEL_AUTO:
+            self.select_kernel(kernel)
+        self.set_seeds(np.arange(self.R, dtype=np.uint64) if seeds is None else seeds, replica_ids)
+        if rates is not None:
+            self.set_rates(rates)
+        if lut is not None:
+            self.set_otf_lut(lut)
+        if init:
+            self.init_state()
+
+    # ---- setup -----------------------------------------------------------------------------------------
+    def select_kernel(self, kind):
+        capi.check(self.L.kmos_b200_select_kernel(self.h, int(kind)))
+
+    def kernel_info(self):
+        info = np.zeros(8, dtype=np.int64)
+        capi.check(self.L.kmos_b200_kernel_info(self.h, info))
+        keys = ("kernel", "replicas_per_cta", "smem_bytes_per_cta", "ctas_per_sm", "sm_count",
+                "state_bytes_per_replica", "table_bytes", "grid")
+        d = dict(zip(keys, (int(x) for x in info)))
+        d["kernel_name"] = {capi.KERNEL_GENERIC: "generic", capi.KERNEL_SMEM: "smem"}[d["kernel"]]
+        return d
+
+    def set_seeds(self, seeds, replica_ids=None):
+        s = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (self.R,)))
+        ids = None
+        if replica_ids is not None:
+            ids = np.ascontiguousarray(replica_ids, dtype=np.uint32)
+            assert ids.size == self.R
+        capi.check(self.L.kmos_b200_set_seeds(self.h, s, ids.ctypes.data_as(C.c_void_p) if ids is not None else None))
+
+    def set_rates(self, rates):
+        r = np.asarray(rates, dtype=np.float64)
+        if r.ndim == 1:
+            r = np.broadcast_to(r, (self.R, self.P))
+        r = np.ascontiguousarray(r)
+        assert r.shape == (self.R, self.P)
+        capi.check(self.L.kmos_b200_set_rates(self.h, r))
+        self._rates_host = r  # keep the pinned-or-not source alive until the async copy is consumed
+
+    def set_rate_const(self, proc, rate, replica=-1):
+        capi.check(self.L.kmos_b200_set_rate_const(self.h, int(replica), int(proc), float(rate)))
+
+    def set_otf_lut(self, lut):
+        t = np.asarray(lut, dtype=np.float64)
+        if t.ndim == 1:
+            t = np.broadcast_to(t, (self.R, t.size))
+        t = np.ascontiguousarray(t)
+        assert t.shape == (self.R, self.model.lut_size)
+        capi.check(self.L.kmos_b200_set_otf_lut(self.h, t))
+        self._lut_host = t
+
+    def init_state(self, layer=None):
+        capi.check(self.L.kmos_b200_init_state(self.h, self.layer if layer is None else int(layer)))
+
+    def set_configuration(self, species, replica=-1, layer=None):
+        s = np.ascontiguousarray(species, dtype=np.int32)
+        assert s.size == (self.volume if replica >= 0 else self.R * self.volume)
+        capi.check(self.L.kmos_b200_set_configuration(self.h, int(replica), s.reshape(-1),
+                                                      self.layer if layer is None else int(layer)))
+
+    # ---- stepping --------------------------------------------------------------------------------------
+    def do_steps(self, n):
+        capi.check(self.L.kmos_b200_do_kmc_steps(self.h, int(n)))
+
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        capi.check(self.L.kmos_b200_batch_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        capi.check(self.L.kmos_b200_synchronize(self.h))
+
+    def timer_start(self):
+        capi.check(self.L.kmos_b200_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        capi.check(self.L.kmos_b200_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    # ---- observables -----------------------------------------------------------------------------------
+    def _get(self, name, shape, dtype):
+        out = np.zeros(shape, dtype=dtype)
+        capi.check(getattr(self.L, "kmos_b200_get_" + name)(self.h, out))
+        return out
+
+    kmc_time = property(lambda self: self._get("kmc_time", self.R, np.float64))
+    kmc_time_step = property(lambda self: self._get("kmc_time_step", self.R, np.float64))
+    kmc_step = property(lambda self: self._get("kmc_step", self.R, np.int64))
+    procstat = property(lambda self: self._get("procstat", (self.R, self.P), np.int64))
+    integ_rates = property(lambda self: self._get("integ_rates", (self.R, self.P), np.float64))
+    nr_of_sites = property(lambda self: self._get("nr_of_sites", (self.R, self.P), np.int32))
+    accum_rates = property(lambda self: self._get("accum_rates", (self.R, self.P), np.float64))
+    rates = property(lambda self: self._get("rates", (self.R, self.P), np.float64))
+    lattice = property(lambda self: self._get("lattice", (self.R, self.volume), np.int32))
+    occupation = property(lambda self: self._get("occupation", (self.R, self.model.n_species, self.model.spuck),
+                                                 np.float64))
+    status = property(lambda self: self._get("status", self.R, np.int32))
+    error_info = property(lambda self: self._get("error_info", (self.R, 5), np.int32))
+
+    def avail_sites(self, replica):
+        out = np.zeros((self.P, self.volume, 2), dtype=np.int32)
+        capi.check(self.L.kmos_b200_get_avail_sites(self.h, int(replica), out))
+        return out
+
+    def tally_words(self):
+        return self.L.kmos_b200_tally_words(self.h)
+
+    def reduce_tallies(self, group_of=None, n_groups=1, dev_ptr=None, want_host=True):
+        """Per-group sums (see include/kmos_b200.h).  dev_ptr: device address to write into (for NCCL)."""
+        words = self.tally_words()
+        g = None
+        if group_of is not None:
+            g = np.ascontiguousarray(group_of, dtype=np.int32)
+            assert g.size == self.R
+        host = np.zeros((n_groups, words)) if want_host else None
+        capi.check(self.L.kmos_b200_reduce_tallies(
+            self.h, g.ctypes.data_as(C.c_void_p) if g is not None else None, int(n_groups),
+            C.c_void_p(dev_ptr) if dev_ptr else None,
+            host.ctypes.data_as(C.c_void_p) if host is not None else None))
+        return host
+
+    def split_tally(self, t):
+        P, nocc = self.P, self.model.n_species * self.model.spuck
+        t = np.asarray(t)
+        return {"procstat": t[..., :P], "integ_rates": t[..., P:2 * P],
+                "occupation": t[..., 2 * P:2 * P + nocc], "kmc_time": t[..., 2 * P + nocc],
+                "kmc_steps": t[..., 2 * P + nocc + 1], "n_replicas": t[..., 2 * P + nocc + 2]}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kmos_b200_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def measure_smem_bandwidth(device=0):
+    """(GB/s, SM clock MHz) of the shared-memory streaming microbenchmark."""
+    gb, mhz = C.c_double(0), C.c_double(0)
+    capi.check(capi.lib().kmos_b200_measure_smem_bandwidth(int(device), C.byref(gb), C.byref(mhz)))
+    return gb.value, mhz.value

@@ -1,0 +1,168 @@
+"""GPU parity: the CUDA engines, called through the C-ABI, against the CPU oracle on the same Philox stream.
+
+Bit-exact: lattice, procstat, nr_of_sites, both planes of avail_sites, kmc_step, status.
+Floating point: kmc_time within 1e-12 relative (north_star), integ_rates within 1e-10 relative
+(device log() vs glibc log() may differ in the last ulp of each time increment).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_model
+from kmos_b200 import capi
+from util import compare_batch, make_inputs, run_oracles
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine():
+    from kmos_b200 import engine
+    return engine
+
+
+SMEM_CASES = [
+    ("mini_101_local_smart", [20, 20], 16, [1, 999, 3000]),
+    ("ab_local_smart", [20, 20], 24, [500, 2500, 3000]),
+    ("zgb_local_smart", [16, 12], 13, [1000, 4000]),
+    ("zgb_local_smart", [64, 64], 3, [3000, 3000]),
+    ("ruo2_local_smart", [20, 20], 32, [2000, 4000, 6000]),
+    ("ruo2_local_smart", [5, 7], 7, [3000, 3000]),
+    ("pairwise_local_smart", [10, 9], 9, [2000, 2000]),
+]
+
+
+@pytest.mark.parametrize("name,size,R,chunks", SMEM_CASES)
+@pytest.mark.parametrize("kernel", ["smem", "generic"])
+def test_local_smart_parity(name, size, R, chunks, kernel):
+    engine = _engine()
+    ir, blob, info = load_model(name)
+    rates, lut, seeds = make_inputs(ir, info, R, seed=len(name))
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    kind = capi.KERNEL_SMEM if kernel == "smem" else capi.KERNEL_GENERIC
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=kind)
+    assert batch.kernel_info()["kernel_name"] == kernel
+    gen = run_oracles(blob, size, rates, lut, seeds, chunks)
+    compare_batch(batch, next(gen), avail_replicas=range(min(R, 3)))
+    for n, oracles in zip(chunks, gen):
+        batch.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(0, R - 1))
+    batch.close()
+
+
+GENERIC_CASES = [
+    ("ab_lat_int", [10, 12], 6, [1500, 1500]),
+    ("ab_otf", [10, 12], 6, [1500, 1500]),
+    ("zgb_lat_int", [12, 12], 5, [2000, 2000]),
+    ("ruo2_lat_int", [8, 8], 5, [1500, 1500]),
+    ("pairwise_lat_int", [16, 16], 8, [2000, 2000]),
+    ("pairwise_otf_otf", [16, 16], 8, [2000, 2000]),
+    ("mini_101_otf", [6, 6], 4, [500, 500]),
+]
+
+
+@pytest.mark.parametrize("name,size,R,chunks", GENERIC_CASES)
+def test_lat_int_and_otf_parity(name, size, R, chunks):
+    engine = _engine()
+    ir, blob, info = load_model(name)
+    rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + 1)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, lut=lut)
+    assert batch.kernel_info()["kernel_name"] == "generic"
+    gen = run_oracles(blob, size, rates, lut, seeds, chunks)
+    compare_batch(batch, next(gen), avail_replicas=(0,))
+    for n, oracles in zip(chunks, gen):
+        batch.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(0, R - 1))
+    batch.close()
+
+
+def test_set_configuration_then_steps():
+    engine = _engine()
+    ir, blob, info = load_model("ruo2_local_smart")
+    R, size = 5, [8, 6]
+    rates, lut, seeds = make_inputs(ir, info, R, seed=5)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates)
+    oracles = next(run_oracles(blob, size, rates, lut, seeds, []))
+    rng = np.random.RandomState(1)
+    spec = rng.randint(0, len(ir["species"]), (R, batch.volume)).astype(np.int32)
+    batch.set_configuration(spec)
+    for r, o in enumerate(oracles):
+        assert o.set_configuration(spec[r]) == 0
+    compare_batch(batch, oracles, avail_replicas=range(R))
+    batch.do_steps(2500)
+    for o in oracles:
+        o.do_steps(2500)
+    compare_batch(batch, oracles, avail_replicas=range(R))
+    # one replica only
+    spec1 = rng.randint(0, len(ir["species"]), batch.volume).astype(np.int32)
+    batch.set_configuration(spec1, replica=3)
+    assert oracles[3].set_configuration(spec1) == 0
+    compare_batch(batch, oracles, avail_replicas=(2, 3))
+
+
+def test_deadlock_is_a_status_not_a_hang():
+    """All rate constants zero: the reference prints its dead-lock message and stops (base.mpy:1296-1305)."""
+    engine = _engine()
+    ir, blob, info = load_model("mini_101_local_smart")
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    for kind in (capi.KERNEL_SMEM, capi.KERNEL_GENERIC):
+        batch = engine.Batch(model, 4, [6, 6], rates=np.zeros((4, 2)), kernel=kind)
+        batch.do_steps(100)
+        assert np.all(batch.status == capi.REPLICA_DEADLOCK)
+        assert np.all(batch.kmc_step == 0)
+        batch.close()
+    # adsorption only: the lattice fills up after exactly 36 events, then nothing is available
+    rates = np.array([[1.0, 0.0]] * 3)
+    batch = engine.Batch(model, 3, [6, 6], rates=rates)
+    batch.do_steps(100)
+    assert np.all(batch.status == capi.REPLICA_DEADLOCK)
+    assert np.all(batch.kmc_step == 36)
+    assert np.all(batch.lattice == 0)  # CO everywhere (species sorted by name: CO=0, empty=1)
+
+
+def test_philox_hook_matches_oracle():
+    from oracle import oracle
+    L = capi.lib()
+    for seed, rep, step in [(1, 0, 0), (2**40 + 17, 123, 2**33 + 5), (99, 4000000000, 77)]:
+        ref = oracle.philox_step(seed, rep, step)
+        got = [L.kmos_b200_philox_next(seed, rep, step, s) for s in range(3)]
+        assert list(ref) == got
+        assert 0 < got[0] <= 1 and 0 <= got[1] < 1 and 0 <= got[2] < 1
+
+
+def test_full_size_ruo2_batch_properties():
+    """BASELINE headline shape (RuO2 20x20, 16384 replicas): size-independent invariants on every replica
+    plus full oracle parity on a sample of replicas."""
+    engine = _engine()
+    ir, blob, info = load_model("ruo2_local_smart")
+    R, size, n = 16384, [20, 20], 2000
+    rates, lut, seeds = make_inputs(ir, info, R, seed=9)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates)
+    assert batch.kernel_info()["kernel_name"] == "smem"
+    batch.do_steps(n)
+    assert np.all(batch.status == 0)
+    assert np.all(batch.kmc_step == n)
+    ps = batch.procstat
+    assert np.all(ps.sum(axis=1) == n)            # every step executed exactly one process
+    occ = batch.occupation
+    np.testing.assert_allclose(occ.sum(axis=1), 1.0, atol=1e-12)  # every site holds exactly one species
+    assert np.all(np.diff(np.sort(batch.kmc_time)) >= 0) and np.all(batch.kmc_time > 0)
+    sample = [0, 1, 4097, 16383]
+    from oracle import oracle
+    lat = batch.lattice
+    ns = batch.nr_of_sites
+    t = batch.kmc_time
+    for r in sample:
+        o = oracle.Oracle(blob, size, seed=int(seeds[r]), replica=r, rates=rates[r])
+        o.do_steps(n)
+        assert np.array_equal(lat[r], o.lattice)
+        assert np.array_equal(ps[r], o.procstat)
+        assert np.array_equal(ns[r], o.nr_of_sites)
+        assert np.array_equal(batch.avail_sites(r), o.avail_sites)
+        assert abs(t[r] - o.kmc_time) <= 1e-12 * o.kmc_time
+    # tallies: one group per 1024 replicas, totals must equal the per-replica sums
+    groups = np.arange(R) // 1024
+    tall = batch.split_tally(batch.reduce_tallies(groups, 16))
+    assert np.array_equal(tall["procstat"].sum(axis=0), ps.sum(axis=0).astype(np.float64))
+    assert np.all(tall["n_replicas"] == 1024) and np.all(tall["kmc_steps"] == 1024 * n)
