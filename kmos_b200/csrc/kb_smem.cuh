@@ -1,17 +1,23 @@
-// kb_smem.cuh -- shared-memory kMC step kernel for sm_100a: one warp steps one replica, the replica's
-// lattice and avail-site tables live in shared memory for the whole launch (TMA bulk-staged from/to HBM),
-// the warps of a CTA share one copy of the model's per-event lane tables.
+// kb_smem.cuh -- shared-memory kMC step kernel for sm_100a: one warp steps one replica; the replica's
+// lattice and (compacted) avail-site tables stay in shared memory for the whole launch, TMA bulk-staged
+// from/to HBM; the warps of a CTA share one copy of the model's per-event lane tables.
 //
 // Reference loop restated per step (kmos/fortran_src/proclist_generic_subroutines.mpy:22-42):
-//   random_number x3            -> per-replica Philox4x32-10 counter stream (kb_common.h)
-//   update_accum_rate           base.mpy:603-623   lane q holds nr_of_sites(q)*rates(q); the serial
-//                                                  left-to-right float64 recurrence is kept (bit parity)
+//   random_number x3            per-replica Philox4x32-10 counter stream, generated 16 steps at a time
+//                               (lane l: step base+l/2, slot l&1) together with -log(ran_time)
+//   update_accum_rate           base.mpy:603-623   products nr_of_sites(q)*rates(q) go through shared
+//                                                  memory; every lane runs the serial left-to-right
+//                                                  float64 recurrence up to its own process (bit parity)
 //   update_clocks               base.mpy:1123-1161
 //   update_integ_rate           base.mpy:626-645   lane-parallel over processes
 //   determine_procsite          base.mpy:1075-1120 + interval_search_real :1234-1338 as a warp ballot
 //   run_proc_nr                 generated put_/take_ routines (kmos/io/__init__.py:305-465, 2219-2409)
-//                               flattened by kmos_b200/devtables.py into rounds of per-process list ops;
-//                               add_proc/del_proc (base.mpy:211-302) run one op per lane
+//                               flattened by kmos_b200/devtables.py into rounds of list ops, one per lane;
+//                               add_proc/del_proc (base.mpy:211-302) on the compact storage below
+//
+// Compact avail-site storage (see devtables.py): plane 1 per arena (two mutually exclusive processes share
+// `cap` uint16 slots, one list from the left, one from the right), plane 2 per exclusivity class and cell
+// (uint16 = member << 13 | position).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -27,6 +33,10 @@ struct KbScalars {
     int32_t pad;
 };
 
+#define KB_POS_BITS 13
+#define KB_POS_MASK 0x1FFFu
+#define KB_RNG_BATCH 16
+
 struct KbSmemParams {
     // model / geometry
     const int32_t* dev;  // SEC_DEVICE in global memory
@@ -34,11 +44,13 @@ struct KbSmemParams {
     int n_proc, spuck, dim;
     int size[3];
     int ncells, volume;
-    uint32_t magic_x, magic_xy;  // umulhi(c, magic) == c / Lx  (resp. c / (Lx*Ly)) for all c < ncells
+    int n_arenas, n_classes, cap;  // cap = ncells + spare slots per arena
+    uint32_t magic_x, magic_xy;    // umulhi(c, magic) == c / Lx  (resp. c / (Lx*Ly)) for all c < ncells
     // batch arrays (global)
     uint8_t* lattice;   // [R][lat_stride]
     int32_t* nsites;    // [R][P]
-    uint16_t* p1;       // [R][row_stride]   row_stride = align16(P*ncells*2)/2
+    uint16_t* image;    // [R][img_bytes/2]  compact planes: arenas then class entries
+    uint16_t* p1;       // canonical planes [R][plane_bytes/2] (pack / unpack kernels only)
     uint16_t* p2;
     const double* rates;
     double* integ;
@@ -47,9 +59,10 @@ struct KbSmemParams {
     int R;
     long long nsteps;
     // shared-memory layout (bytes)
-    int tab_bytes, rep_bytes, off_p2, off_lat, off_ns, off_mbar;
-    int lat_stride;       // bytes, multiple of 16
-    int plane_bytes;      // bytes of one avail plane, multiple of 16
+    int tab_bytes, rep_bytes, off_p2, off_lat, off_ns, off_prod, off_mbar;
+    int lat_stride;   // bytes, multiple of 16
+    int img_bytes;    // bytes of the compact image (both planes), multiple of 16
+    int plane_bytes;  // bytes of one canonical plane, multiple of 16
     int use_bulk;
 };
 
@@ -96,17 +109,75 @@ __device__ __forceinline__ void kb_bulk_commit_wait() {
 }
 __device__ __forceinline__ void kb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ int kb_unpack_s8(uint32_t w, int shift) { return (int)(int8_t)((w >> shift) & 255u); }
+__device__ __forceinline__ int kb_s8(uint32_t w, int shift) { return (int)(int8_t)((w >> shift) & 255u); }
 
+// slot index of position k (0-based) of a list inside its arena
+__device__ __forceinline__ int kb_slot(int arena, int dir, int cap, int k) {
+    return arena * cap + (dir ? cap - 1 - k : k);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// canonical <-> compact conversion (one warp per replica, runs between engine switches only)
+// ---------------------------------------------------------------------------------------------------
+__global__ void kb_pack_kernel(const KbSmemParams prm) {
+    const int lane = threadIdx.x & 31;
+    const int rep = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (rep >= prm.R) return;
+    const int P = prm.n_proc, C = prm.ncells, cap = prm.cap;
+    const int32_t* procinfo = prm.dev + prm.dev[9];
+    uint16_t* img = prm.image + (size_t)rep * (prm.img_bytes / 2);
+    uint16_t* cp2 = img + (size_t)prm.n_arenas * cap;
+    const uint16_t* g1 = prm.p1 + (size_t)rep * (prm.plane_bytes / 2);
+    const int32_t* ns = prm.nsites + (size_t)rep * P;
+    for (int i = lane; i < prm.img_bytes / 2; i += 32) img[i] = 0;
+    __syncwarp();
+    for (int q = 0; q < P; ++q) {
+        const uint32_t pi = (uint32_t)procinfo[q];
+        const int arena = pi & 63, dir = (pi >> 6) & 1, cls = (pi >> 7) & 31, member = (pi >> 12) & 7;
+        const int n = ns[q];
+        for (int k = lane; k < n; k += 32) {
+            const int cell = g1[(size_t)q * C + k];
+            img[kb_slot(arena, dir, cap, k)] = (uint16_t)cell;
+            cp2[(size_t)cls * C + cell] = (uint16_t)((member << KB_POS_BITS) | (k + 1));
+        }
+    }
+}
+
+__global__ void kb_unpack_kernel(const KbSmemParams prm) {
+    const int lane = threadIdx.x & 31;
+    const int rep = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (rep >= prm.R) return;
+    const int P = prm.n_proc, C = prm.ncells, cap = prm.cap;
+    const int32_t* procinfo = prm.dev + prm.dev[9];
+    const uint16_t* img = prm.image + (size_t)rep * (prm.img_bytes / 2);
+    uint16_t* g1 = prm.p1 + (size_t)rep * (prm.plane_bytes / 2);
+    uint16_t* g2 = prm.p2 + (size_t)rep * (prm.plane_bytes / 2);
+    const int32_t* ns = prm.nsites + (size_t)rep * P;
+    for (int i = lane; i < prm.plane_bytes / 2; i += 32) { g1[i] = 0; g2[i] = 0; }
+    __syncwarp();
+    for (int q = 0; q < P; ++q) {
+        const uint32_t pi = (uint32_t)procinfo[q];
+        const int arena = pi & 63, dir = (pi >> 6) & 1;
+        const int n = ns[q];
+        for (int k = lane; k < n; k += 32) {
+            const int cell = img[kb_slot(arena, dir, cap, k)];
+            g1[(size_t)q * C + k] = (uint16_t)cell;
+            g2[(size_t)q * C + cell] = (uint16_t)(k + 1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// step kernel
+// ---------------------------------------------------------------------------------------------------
 struct KbCellCtx {
-    int Lx, Ly, Lz, dim, spuck;
+    int Lx, Ly, Lz, dim;
     uint32_t magic_x, magic_xy;
     int x, y, z;
     __device__ __forceinline__ void decode(int cell) {
         if (dim >= 3) {
-            int LxLy = Lx * Ly;
             z = (int)__umulhi((uint32_t)cell, magic_xy);
-            cell -= z * LxLy;
+            cell -= z * Lx * Ly;
         } else {
             z = 0;
         }
@@ -118,20 +189,20 @@ struct KbCellCtx {
             x = cell;
         }
     }
-    // cell index of (x+dx, y+dy, z+dz) with periodic wrap; |d*| <= L* is checked at batch creation
+    // cell index of (x+dx, y+dy, z+dz) with periodic wrap; |d*| < L* is checked at batch creation
     __device__ __forceinline__ int cell_at(uint32_t packed) const {
-        int xx = x + kb_unpack_s8(packed, 0);
+        int xx = x + kb_s8(packed, 0);
         xx += (xx < 0) ? Lx : 0;
         xx -= (xx >= Lx) ? Lx : 0;
         int c = xx;
         if (dim >= 2) {
-            int yy = y + kb_unpack_s8(packed, 8);
+            int yy = y + kb_s8(packed, 8);
             yy += (yy < 0) ? Ly : 0;
             yy -= (yy >= Ly) ? Ly : 0;
             c += Lx * yy;
         }
         if (dim >= 3) {
-            int zz = z + kb_unpack_s8(packed, 16);
+            int zz = z + kb_s8(packed, 16);
             zz += (zz < 0) ? Lz : 0;
             zz -= (zz >= Lz) ? Lz : 0;
             c += Lx * Ly * zz;
@@ -140,8 +211,8 @@ struct KbCellCtx {
     }
 };
 
-// PPL: processes per lane (1: P <= 32, 2: P <= 64)
-template <int PPL>
+// PPL: processes per lane (1: P <= 32, 2: P <= 64);  NCOND: largest number of dynamic probes of an add
+template <int PPL, int NCOND>
 __global__ void kb_smem_kernel(const KbSmemParams prm) {
     extern __shared__ __align__(128) unsigned char kb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -152,26 +223,27 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
     const int rep = blockIdx.x * wpc + warp;
     if (rep >= prm.R) return;  // no block-wide barrier below this line
 
-    const int32_t* events = tab + tab[3];
+    const uint4* events = reinterpret_cast<const uint4*>(tab + tab[3]);
     const uint32_t* ops = reinterpret_cast<const uint32_t*>(tab + tab[4]);
-    const uint32_t* anchors = reinterpret_cast<const uint32_t*>(tab + tab[6]);
-    const uint32_t* conds = reinterpret_cast<const uint32_t*>(tab + tab[8]);
+    const uint32_t* offsets = reinterpret_cast<const uint32_t*>(tab + tab[7]);
+    const uint32_t* procinfo = reinterpret_cast<const uint32_t*>(tab + tab[9]);
+    const int n_off = tab[8];
+    constexpr int STRIDE = 1 + NCOND;
 
     unsigned char* base = kb_smem + prm.tab_bytes + (size_t)warp * prm.rep_bytes;
     uint16_t* p1 = reinterpret_cast<uint16_t*>(base);
     uint16_t* p2 = reinterpret_cast<uint16_t*>(base + prm.off_p2);
     uint8_t* lat = base + prm.off_lat;
     int32_t* nS = reinterpret_cast<int32_t*>(base + prm.off_ns);
+    double* prodS = reinterpret_cast<double*>(base + prm.off_prod);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(base + prm.off_mbar);
 
-    const int P = prm.n_proc, C = prm.ncells;
-    const size_t row_elems = (size_t)prm.plane_bytes / 2;
-    uint16_t* g_p1 = prm.p1 + (size_t)rep * row_elems;
-    uint16_t* g_p2 = prm.p2 + (size_t)rep * row_elems;
+    const int P = prm.n_proc, C = prm.ncells, cap = prm.cap, spuck = prm.spuck;
+    uint16_t* g_img = prm.image + (size_t)rep * (prm.img_bytes / 2);
     uint8_t* g_lat = prm.lattice + (size_t)rep * prm.lat_stride;
     int32_t* g_ns = prm.nsites + (size_t)rep * P;
 
-    // ---- stage the replica into shared memory ------------------------------------------------------
+    // ---- stage the replica into shared memory (the image is laid out exactly like p1|p2 here) ---------
     if (prm.use_bulk) {
         if (lane == 0) {
             kb_mbar_init(mbar, 1);
@@ -179,18 +251,15 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         }
         __syncwarp();
         if (lane == 0) {
-            kb_mbar_expect_tx(mbar, (uint32_t)(2 * prm.plane_bytes + prm.lat_stride));
-            kb_bulk_g2s(p1, g_p1, (uint32_t)prm.plane_bytes, mbar);
-            kb_bulk_g2s(p2, g_p2, (uint32_t)prm.plane_bytes, mbar);
+            kb_mbar_expect_tx(mbar, (uint32_t)(prm.img_bytes + prm.lat_stride));
+            kb_bulk_g2s(p1, g_img, (uint32_t)prm.img_bytes, mbar);
             kb_bulk_g2s(lat, g_lat, (uint32_t)prm.lat_stride, mbar);
         }
         kb_mbar_wait(mbar, 0);
     } else {
-        const uint4* s1 = reinterpret_cast<const uint4*>(g_p1);
-        const uint4* s2 = reinterpret_cast<const uint4*>(g_p2);
+        const uint4* s1 = reinterpret_cast<const uint4*>(g_img);
         uint4* d1 = reinterpret_cast<uint4*>(p1);
-        uint4* d2 = reinterpret_cast<uint4*>(p2);
-        for (int i = lane; i < prm.plane_bytes / 16; i += 32) { d1[i] = s1[i]; d2[i] = s2[i]; }
+        for (int i = lane; i < prm.img_bytes / 16; i += 32) d1[i] = s1[i];
         const uint4* sl = reinterpret_cast<const uint4*>(g_lat);
         uint4* dl = reinterpret_cast<uint4*>(lat);
         for (int i = lane; i < prm.lat_stride / 16; i += 32) dl[i] = sl[i];
@@ -215,41 +284,65 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
     int err0 = 0, err1 = 0, err2 = 0, err3 = 0, err4 = 0;
 
     KbCellCtx cc;
-    cc.Lx = prm.size[0]; cc.Ly = prm.size[1]; cc.Lz = prm.size[2]; cc.dim = prm.dim; cc.spuck = prm.spuck;
+    cc.Lx = prm.size[0]; cc.Ly = prm.size[1]; cc.Lz = prm.size[2]; cc.dim = prm.dim;
     cc.magic_x = prm.magic_x; cc.magic_xy = prm.magic_xy;
     const uint32_t k0 = (uint32_t)sc.seed, k1 = (uint32_t)(sc.seed >> 32);
+    const uint32_t my_off = lane < n_off ? offsets[lane] : 0u;
+    const int P32 = (min(P, 32) + 3) & ~3;  // entries of the first chain pass (prodS is zero padded)
+    const int lastp = P - 1;
+
+    double rng_a = 0.0, rng_b = 0.0;  // even lanes: (-log(ran_time), ran_proc); odd lanes: (ran_site, -)
 
     for (long long it = 0; it < prm.nsteps && status == KB_OK; ++it) {
-        // -- the step's three uniforms: lane parity picks the Philox slot, results are broadcast
-        uint32_t rnd[4];
-        kb_philox4x32_10((uint32_t)kmc_step, (uint32_t)((unsigned long long)kmc_step >> 32), sc.replica,
-                         (uint32_t)(lane & 1), k0, k1, rnd);
-        const uint32_t a0w = __shfl_sync(KB_FULL, rnd[0], 0), a1w = __shfl_sync(KB_FULL, rnd[1], 0);
-        const uint32_t a2w = __shfl_sync(KB_FULL, rnd[2], 0), a3w = __shfl_sync(KB_FULL, rnd[3], 0);
-        const uint32_t b0w = __shfl_sync(KB_FULL, rnd[0], 1), b1w = __shfl_sync(KB_FULL, rnd[1], 1);
-        const double ran_time = (double)(((((uint64_t)a1w << 32) | a0w) >> 11) + 1) * 0x1.0p-53;
-        const double ran_proc = (double)((((uint64_t)a3w << 32) | a2w) >> 11) * 0x1.0p-53;
-        const double ran_site = (double)((((uint64_t)b1w << 32) | b0w) >> 11) * 0x1.0p-53;
+        const int sub = (int)(it & (KB_RNG_BATCH - 1));
+        if (sub == 0) {
+            // 16 steps of uniforms at once: lane l serves step kmc_step + l/2, Philox slot l&1
+            const unsigned long long st = (unsigned long long)kmc_step + (unsigned)(lane >> 1);
+            uint32_t rnd[4];
+            kb_philox4x32_10((uint32_t)st, (uint32_t)(st >> 32), sc.replica, (uint32_t)(lane & 1), k0, k1, rnd);
+            const double u0 = (double)(((((uint64_t)rnd[1] << 32) | rnd[0]) >> 11) + (uint64_t)((lane & 1) ^ 1)) * 0x1.0p-53;
+            const double u1 = (double)((((uint64_t)rnd[3] << 32) | rnd[2]) >> 11) * 0x1.0p-53;
+            rng_a = (lane & 1) ? u0 : -log(u0);  // odd: ran_site in [0,1); even: -log(ran_time), ran_time in (0,1]
+            rng_b = u1;                          // even: ran_proc
+        }
+        const double neg_log_u = __shfl_sync(KB_FULL, rng_a, 2 * sub);
+        const double ran_proc = __shfl_sync(KB_FULL, rng_b, 2 * sub);
+        const double ran_site = __shfl_sync(KB_FULL, rng_a, 2 * sub + 1);
 
-        // -- update_accum_rate: serial float64 recurrence over processes, values exchanged by shuffle
+        // -- update_accum_rate: products through shared memory, serial float64 recurrence per lane
         const int n0 = has0 ? nS[q0] : 0;
         const int n1 = has1 ? nS[q1] : 0;
         const double pr0 = __dmul_rn((double)n0, rate0);
         const double pr1 = __dmul_rn((double)n1, rate1);
-        double acc = 0.0, acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 4
-        for (int i = 0; i < P; ++i) {
-            const double x = __shfl_sync(KB_FULL, (PPL == 2 && i >= 32) ? pr1 : pr0, i & 31);
-            acc = __dadd_rn(acc, x);
-            if ((i & 31) == lane) {
-                if (PPL == 2 && i >= 32) acc1 = acc; else acc0 = acc;
+        prodS[q0] = pr0;
+        if (PPL == 2) prodS[q1] = pr1;
+        __syncwarp();
+        double acc0 = 0.0;
+        {
+            const double2* pp = reinterpret_cast<const double2*>(prodS);
+            for (int j = 0; j < P32; j += 4) {
+                const double2 a = pp[j >> 1], b = pp[(j >> 1) + 1];
+                if (j <= lane) acc0 = __dadd_rn(acc0, a.x);
+                if (j + 1 <= lane) acc0 = __dadd_rn(acc0, a.y);
+                if (j + 2 <= lane) acc0 = __dadd_rn(acc0, b.x);
+                if (j + 3 <= lane) acc0 = __dadd_rn(acc0, b.y);
             }
         }
-        const double total = acc;
+        double acc1 = 0.0;
+        if (PPL == 2) {
+            acc1 = __shfl_sync(KB_FULL, acc0, 31);
+            const double2* pp = reinterpret_cast<const double2*>(prodS);
+            for (int j = 32; j < P; j += 2) {
+                const double2 a = pp[j >> 1];
+                if (j <= q1) acc1 = __dadd_rn(acc1, a.x);
+                if (j + 1 <= q1) acc1 = __dadd_rn(acc1, a.y);
+            }
+        }
+        const double total = __shfl_sync(KB_FULL, (PPL == 2 && lastp >= 32) ? acc1 : acc0, lastp & 31);
         if (!(total > 0.0)) { status = KB_DEADLOCK; break; }
 
         // -- update_clocks / update_integ_rate
-        kmc_dt = -log(ran_time) / total;
+        kmc_dt = neg_log_u / total;
         kmc_time = __dadd_rn(kmc_time, kmc_dt);
         kmc_step += 1;
         integ0 = __dadd_rn(integ0, __dmul_rn(pr0, kmc_dt));
@@ -271,66 +364,75 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         if (nsel <= 0) { status = KB_DEADLOCK; break; }
         int k = (int)__dadd_rn(1.0, __dmul_rn(ran_site, (double)nsel));
         k = min(k, nsel);
-        const int cell = (int)p1[pidx * C + k - 1];
+        const uint32_t spi = procinfo[pidx];
+        const int cell = (int)p1[kb_slot((int)(spi & 63u), (int)((spi >> 6) & 1u), cap, k - 1)];
         if ((pidx & 31) == lane) {
             if (PPL == 2 && pidx >= 32) ps1 += 1; else ps0 += 1;
         }
 
-        // -- run_proc_nr(pidx+1, site): lattice writes, then rounds of per-process list operations
-        const int32_t* ev = events + pidx * KB_DEV_EVENT_STRIDE;
-        const int ops_start = ev[0], n_rounds = ev[1], n_writes = ev[2];
+        // -- run_proc_nr(pidx+1, site): lattice writes, then rounds of list operations
+        const uint4 eh = events[2 * pidx], ew = events[2 * pidx + 1];
+        const int ops_start = (int)(eh.x & 0xFFFFu), n_rounds = (int)((eh.x >> 16) & 15u), n_writes = (int)((eh.x >> 20) & 15u);
         cc.decode(cell);
-        if (lane < n_writes) {
-            const uint32_t ws = (uint32_t)ev[4 + KB_DEV_MAX_ROUNDS + 2 * lane];
-            const uint32_t on = (uint32_t)ev[4 + KB_DEV_MAX_ROUNDS + 2 * lane + 1];
-            const int idx = cc.cell_at(ws) * cc.spuck + (int)(ws >> 24) - 1;
-            const int found = lat[idx];
-            if (found != (int)(on & 255u)) {  // replace_species consistency check (base.mpy:1205)
-                status = KB_SPECIES_MISMATCH;
-                err0 = (int)(on & 255u); err1 = (int)(on >> 8); err2 = found; err3 = idx + 1; err4 = (int)(kmc_step - 1);
-            } else {
-                lat[idx] = (uint8_t)(on >> 8);
+        const int nb = cc.cell_at(my_off);  // lane l: cell index of neighbour offset l
+        {
+            const uint32_t w = lane == 0 ? ew.x : (lane == 1 ? ew.y : (lane == 2 ? ew.z : ew.w));
+            const int wcell = __shfl_sync(KB_FULL, nb, (int)(w & 31u));
+            if (lane < n_writes) {
+                const int idx = wcell * spuck + (int)((w >> 5) & 7u) - 1;
+                const int found = lat[idx], oldsp = (int)((w >> 8) & 15u), newsp = (int)((w >> 12) & 15u);
+                if (found != oldsp) {  // replace_species consistency check (base.mpy:1205)
+                    status = KB_SPECIES_MISMATCH;
+                    err0 = oldsp; err1 = newsp; err2 = found; err3 = idx + 1; err4 = (int)(kmc_step - 1);
+                } else {
+                    lat[idx] = (uint8_t)newsp;
+                }
             }
         }
         int start = 0;
+        const unsigned long long ends = ((unsigned long long)eh.z << 32) | eh.y;
         for (int r = 0; r < n_rounds; ++r) {
-            const int endr = ev[4 + r];
+            const int endr = (int)((ends >> (8 * r)) & 255u);
             const int i = start + lane;
-            if (i < endr) {
-                const uint32_t w0 = ops[2 * (ops_start + i)], w1 = ops[2 * (ops_start + i) + 1];
-                const int kind = (int)(w0 & 15u), q = (int)((w0 >> 4) & 0xFFFu) - 1;
-                const int ncond = (int)(w0 >> 24);
-                const int ca = cc.cell_at(anchors[(w0 >> 16) & 255u]);
-                const int row = q * C;
-                if (kind == KB_KIND_ADD) {
-                    bool ok = true;
-                    for (int j = 0; j < ncond; ++j) {
-                        const uint32_t ci = (w1 >> (8 * j)) & 255u;
-                        const uint32_t cs = conds[2 * ci], mask = conds[2 * ci + 1];
-                        const int sidx = cc.cell_at(cs) * cc.spuck + (int)(cs >> 24) - 1;
-                        const uint32_t sp = lat[sidx];
-                        ok = ok && (sp < 32u) && ((mask >> sp) & 1u);
-                    }
-                    if (ok) {  // add_proc (base.mpy:268-302)
-                        const int nq = nS[q];
-                        if (nq >= C || p2[row + ca] != 0) {
-                            status = KB_CAPACITY;
-                        } else {
-                            p1[row + nq] = (uint16_t)ca;
-                            p2[row + ca] = (uint16_t)(nq + 1);
-                            nS[q] = nq + 1;
-                        }
+            const bool valid = i < endr;
+            const uint32_t h = valid ? ops[(ops_start + i) * STRIDE] : 0u;
+            const int ca = __shfl_sync(KB_FULL, nb, (int)((h >> 4) & 31u));
+            bool ok = valid;
+            const int ncond = (int)((h >> 1) & 7u);
+#pragma unroll
+            for (int j = 0; j < NCOND; ++j) {
+                const uint32_t cw = (valid && j < ncond) ? ops[(ops_start + i) * STRIDE + 1 + j] : 0u;
+                const int ccell = __shfl_sync(KB_FULL, nb, (int)(cw & 31u));
+                if (valid && j < ncond) {
+                    const uint32_t sp = lat[ccell * spuck + (int)((cw >> 5) & 7u) - 1];
+                    ok = ok && (((cw >> 8) >> sp) & 1u);
+                }
+            }
+            if (ok) {
+                const int q = (int)((h >> 9) & 63u), cls = (int)((h >> 15) & 31u);
+                const uint32_t member = (h >> 20) & 7u;
+                const int arena = (int)((h >> 23) & 63u), dir = (int)((h >> 29) & 1u);
+                uint16_t* entry = p2 + cls * C;
+                if (h & 1u) {  // add_proc (base.mpy:268-302)
+                    const int nq = nS[q];
+                    if (nq >= C || entry[ca] != 0) {
+                        status = KB_CAPACITY;
+                    } else {
+                        p1[kb_slot(arena, dir, cap, nq)] = (uint16_t)ca;
+                        entry[ca] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)(nq + 1));
+                        nS[q] = nq + 1;
                     }
                 } else {  // guarded del_proc (base.mpy:211-265)
-                    const int pos = p2[row + ca];
-                    if (pos != 0) {
+                    const uint32_t e = entry[ca];
+                    if ((e >> KB_POS_BITS) == member) {
+                        const int pos = (int)(e & KB_POS_MASK);
                         const int nq = nS[q];
-                        const uint16_t last = p1[row + nq - 1];
+                        const uint16_t last = p1[kb_slot(arena, dir, cap, nq - 1)];
                         if (pos < nq) {
-                            p1[row + pos - 1] = last;
-                            p2[row + last] = (uint16_t)pos;
+                            p1[kb_slot(arena, dir, cap, pos - 1)] = last;
+                            entry[last] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)pos);
                         }
-                        p2[row + ca] = 0;
+                        entry[ca] = 0;
                         nS[q] = nq - 1;
                     }
                 }
@@ -340,7 +442,7 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         }
         __syncwarp();  // lattice writes of an event without ops must be visible to the next step
         // a lane-local failure (species mismatch / capacity) stops the replica for every lane
-        status = __reduce_max_sync(KB_FULL, status);
+        if (__any_sync(KB_FULL, status != KB_OK)) status = __reduce_max_sync(KB_FULL, status);
     }
     status = __reduce_max_sync(KB_FULL, status);
 
@@ -350,17 +452,14 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         kb_fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            kb_bulk_s2g(g_p1, p1, (uint32_t)prm.plane_bytes);
-            kb_bulk_s2g(g_p2, p2, (uint32_t)prm.plane_bytes);
+            kb_bulk_s2g(g_img, p1, (uint32_t)prm.img_bytes);
             kb_bulk_s2g(g_lat, lat, (uint32_t)prm.lat_stride);
             kb_bulk_commit_wait();
         }
     } else {
-        uint4* s1 = reinterpret_cast<uint4*>(g_p1);
-        uint4* s2 = reinterpret_cast<uint4*>(g_p2);
+        uint4* s1 = reinterpret_cast<uint4*>(g_img);
         const uint4* d1 = reinterpret_cast<const uint4*>(p1);
-        const uint4* d2 = reinterpret_cast<const uint4*>(p2);
-        for (int i = lane; i < prm.plane_bytes / 16; i += 32) { s1[i] = d1[i]; s2[i] = d2[i]; }
+        for (int i = lane; i < prm.img_bytes / 16; i += 32) s1[i] = d1[i];
         uint4* sl = reinterpret_cast<uint4*>(g_lat);
         const uint4* dl = reinterpret_cast<const uint4*>(lat);
         for (int i = lane; i < prm.lat_stride / 16; i += 32) sl[i] = dl[i];

@@ -59,13 +59,15 @@ struct kmos_b200_batch {
     int64_t* procstat;
     KbScalars* sc;
     double *rates_matrix, *accum_proc, *lut;
+    uint16_t* image;     // compact avail planes of the shared-memory engine [R][img_bytes/2]
+    bool compact_valid;  // true: `image` holds the avail tables, p1/p2 are stale; false: the other way round
     double* tally;
     int32_t* group_of;
     int tally_groups;
     // kernel choice
     int kernel;  // KMOS_B200_KERNEL_GENERIC / SMEM
     KbSmemParams sp;
-    int wpc, ctas_per_sm, sm_count, smem_bytes, ppl;
+    int wpc, ctas_per_sm, sm_count, smem_bytes, ppl, ncond;
     bool smem_ok;
     std::string smem_reason;
 };
@@ -96,21 +98,17 @@ extern "C" int kmos_b200_model_create(const int32_t* blob, int64_t n_words, kmos
                            "model_create: a process is registered on several site types (per-cell avail layout)");
         }
     if (m->h.n_species > 32) { delete m; return set_err(KMOS_B200_ERR_UNSUPPORTED, "more than 32 species"); }
-    m->dev_supported = m->h.dev && m->h.dev_len >= 13 && m->h.dev[1] == 1;
+    m->dev_supported = m->h.dev && m->h.dev_len >= 16 && m->h.dev[0] == 2 && m->h.dev[1] == 1;
     m->max_off[0] = m->max_off[1] = m->max_off[2] = 0;
     if (m->dev_supported) {
         const int32_t* d = m->h.dev;
-        auto upd = [&](uint32_t w) {
+        for (int i = 0; i < d[8]; ++i) {
+            uint32_t w = (uint32_t)d[d[7] + i];
             for (int a = 0; a < 3; ++a) {
-                int v = (int)(int8_t)((w >> (8 * a)) & 255u);
-                if (abs(v) > m->max_off[a]) m->max_off[a] = abs(v);
+                int v = abs((int)(int8_t)((w >> (8 * a)) & 255u));
+                if (v > m->max_off[a]) m->max_off[a] = v;
             }
-        };
-        for (int i = 0; i < d[7]; ++i) upd((uint32_t)d[d[6] + i]);
-        for (int i = 0; i < d[9]; ++i) upd((uint32_t)d[d[8] + 2 * i]);
-        for (int e = 0; e < d[2]; ++e)
-            for (int w = 0; w < d[d[3] + e * KB_DEV_EVENT_STRIDE + 2]; ++w)
-                upd((uint32_t)d[d[3] + e * KB_DEV_EVENT_STRIDE + 4 + KB_DEV_MAX_ROUNDS + 2 * w]);
+        }
     }
     *out = m;
     return KMOS_B200_OK;
@@ -243,25 +241,33 @@ static void plan_smem(kmos_b200_batch* b) {
     const kmos_b200_model* m = b->model;
     b->smem_ok = false;
     if (m->h.backend != KB_BACKEND_LOCAL_SMART || !m->dev_supported) { b->smem_reason = "no device tables for this model/backend"; return; }
-    if (b->idx32) { b->smem_reason = "more than 65535 cells"; return; }
+    if (b->g.ncells > (int)KB_POS_MASK) { b->smem_reason = "more than 8191 cells"; return; }
     if (m->h.n_proc > 64) { b->smem_reason = "more than 64 processes"; return; }
+    // an anchor cell must identify its neighbour offset uniquely: no two offsets may alias under wrap
     for (int a = 0; a < m->h.dim; ++a)
-        if (m->max_off[a] > b->g.size[a]) { b->smem_reason = "lattice smaller than the interaction range"; return; }
+        if (2 * m->max_off[a] >= b->g.size[a]) { b->smem_reason = "lattice smaller than twice the interaction range"; return; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, b->device) != cudaSuccess) { b->smem_reason = "no device properties"; return; }
     b->sm_count = prop.multiProcessorCount;
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
     const int per_sm = (int)prop.sharedMemPerMultiprocessor;
+    const int32_t* d = m->h.dev;
     KbSmemParams& sp = b->sp;
     memset(&sp, 0, sizeof sp);
     sp.dev_words = m->h.dev_len;
     sp.tab_bytes = (int)align_up((size_t)sp.dev_words * 4, 128);
+    sp.n_classes = d[10]; sp.n_arenas = d[11];
+    sp.cap = (b->g.ncells + d[13] + 1) & ~1;  // spare slots: lists of an arena may overlap transiently by
+                                              // at most the number of adds of one event
     sp.plane_bytes = (int)b->plane_bytes;
     sp.lat_stride = b->lat_stride;
-    sp.off_p2 = sp.plane_bytes;
-    sp.off_lat = 2 * sp.plane_bytes;
+    const size_t img = ((size_t)sp.n_arenas * sp.cap + (size_t)sp.n_classes * b->g.ncells) * 2;
+    sp.img_bytes = (int)align_up(img, 16);
+    sp.off_p2 = sp.n_arenas * sp.cap * 2;
+    sp.off_lat = sp.img_bytes;
     sp.off_ns = sp.off_lat + sp.lat_stride;
-    sp.off_mbar = (int)align_up((size_t)sp.off_ns + 4 * m->h.n_proc, 16);
+    sp.off_prod = (int)align_up((size_t)sp.off_ns + 4 * m->h.n_proc, 16);
+    sp.off_mbar = sp.off_prod + 8 * (m->h.n_proc > 32 ? 64 : 32);
     sp.rep_bytes = (int)align_up((size_t)sp.off_mbar + 16, 128);
     int best_w = 0, best_c = 0, best_total = 0;
     for (int w = 1; w <= 16; ++w) {
@@ -271,15 +277,23 @@ static void plan_smem(kmos_b200_batch* b) {
         if (c > 32) c = 32;
         if (c * w > 64) c = 64 / w;
         if (c < 1) continue;
-        if (c * w > best_total) { best_total = c * w; best_w = w; best_c = c; }
+        if (c * w >= best_total) { best_total = c * w; best_w = w; best_c = c; }  // ties: fewer table copies
     }
     if (!best_w) { b->smem_reason = "one replica does not fit in shared memory"; return; }
+    const char* wenv = getenv("KMOS_B200_WARPS_PER_CTA");
+    if (wenv && atoi(wenv) > 0 && sp.tab_bytes + atoi(wenv) * sp.rep_bytes <= max_smem) {
+        best_w = atoi(wenv);
+        best_c = per_sm / (sp.tab_bytes + best_w * sp.rep_bytes + 1024);
+        if (best_c < 1) best_c = 1;
+    }
     b->wpc = best_w; b->ctas_per_sm = best_c; b->smem_bytes = sp.tab_bytes + best_w * sp.rep_bytes;
     b->ppl = m->h.n_proc > 32 ? 2 : 1;
+    b->ncond = d[14];
+    if (b->ncond > 4) { b->smem_reason = "more than 4 probes per add"; return; }
     int Lx = b->g.size[0], LxLy = b->g.size[0] * b->g.size[1];
+    if (Lx == 1 || LxLy == 1) { b->smem_reason = "degenerate lattice"; return; }
     sp.magic_x = (uint32_t)((0x100000000ull / (uint64_t)Lx) + 1);
     sp.magic_xy = (uint32_t)((0x100000000ull / (uint64_t)LxLy) + 1);
-    if (Lx == 1 || LxLy == 1) { b->smem_reason = "degenerate lattice"; return; }
     if (!magic_ok(sp.magic_x, Lx, b->g.ncells) || !magic_ok(sp.magic_xy, LxLy, b->g.ncells)) { b->smem_reason = "no exact reciprocal"; return; }
     sp.n_proc = m->h.n_proc; sp.spuck = m->h.spuck; sp.dim = m->h.dim;
     for (int a = 0; a < 3; ++a) sp.size[a] = b->g.size[a];
@@ -350,6 +364,9 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     CU(cudaMemcpy(b->sc, sc.data(), sc.size() * sizeof(KbScalars), cudaMemcpyHostToDevice));
     b->tally = nullptr; b->group_of = nullptr; b->tally_groups = 0;
     plan_smem(b);
+    b->image = nullptr;
+    b->compact_valid = false;
+    if (b->smem_ok) CU(cudaMalloc(&b->image, (size_t)R * b->sp.img_bytes));
     b->kernel = b->smem_ok ? KMOS_B200_KERNEL_SMEM : KMOS_B200_KERNEL_GENERIC;
     *out = b;
     return KMOS_B200_OK;
@@ -361,7 +378,7 @@ extern "C" void kmos_b200_batch_destroy(kmos_b200_batch* b) {
     cudaStreamSynchronize(b->stream);
     cudaFree(b->d_blob); cudaFree(b->lattice); cudaFree(b->p1); cudaFree(b->p2); cudaFree(b->nsites);
     cudaFree(b->rates); cudaFree(b->integ); cudaFree(b->accum); cudaFree(b->procstat); cudaFree(b->sc);
-    cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->group_of);
+    cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->group_of); cudaFree(b->image);
     cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
     cudaStreamDestroy(b->own_stream);
     delete b;
@@ -484,8 +501,39 @@ extern "C" int kmos_b200_set_otf_lut(kmos_b200_batch* b, const double* lut) {
     return KMOS_B200_OK;
 }
 
+static KbSmemParams smem_params(const kmos_b200_batch* b) {
+    KbSmemParams sp = b->sp;
+    sp.dev = b->d.dev;
+    sp.lattice = b->lattice; sp.nsites = b->nsites; sp.image = b->image;
+    sp.p1 = (uint16_t*)b->p1; sp.p2 = (uint16_t*)b->p2;
+    sp.rates = b->rates; sp.integ = b->integ; sp.procstat = b->procstat; sp.sc = b->sc;
+    sp.R = b->R;
+    return sp;
+}
+
+// The avail tables live either in the canonical planes p1/p2 (generic engine, getters) or in the compact
+// image (shared-memory engine); convert lazily when the other representation is needed.
+static int ensure_canonical(kmos_b200_batch* b) {
+    if (!b->compact_valid) return KMOS_B200_OK;
+    CU(cudaSetDevice(b->device));
+    kb_unpack_kernel<<<(b->R + 3) / 4, 128, 0, b->stream>>>(smem_params(b));
+    CU(cudaGetLastError());
+    b->compact_valid = false;
+    return KMOS_B200_OK;
+}
+static int ensure_compact(kmos_b200_batch* b) {
+    if (b->compact_valid) return KMOS_B200_OK;
+    CU(cudaSetDevice(b->device));
+    kb_pack_kernel<<<(b->R + 3) / 4, 128, 0, b->stream>>>(smem_params(b));
+    CU(cudaGetLastError());
+    b->compact_valid = true;
+    return KMOS_B200_OK;
+}
+
 static int launch_generic(kmos_b200_batch* b, int mode, long long n, int layer, int only_rep) {
     CU(cudaSetDevice(b->device));
+    int rc = ensure_canonical(b);
+    if (rc) return rc;
     KbBatchView v = batch_view(b);
     const int threads = 64;
     const int blocks = (b->R + threads - 1) / threads;
@@ -524,21 +572,28 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     if (n == 0) return KMOS_B200_OK;
     if (b->kernel == KMOS_B200_KERNEL_GENERIC) return launch_generic(b, KB_MODE_STEPS, n, 0, -1);
     CU(cudaSetDevice(b->device));
-    KbSmemParams sp = b->sp;
-    sp.dev = b->d.dev;
-    sp.lattice = b->lattice; sp.nsites = b->nsites;
-    sp.p1 = (uint16_t*)b->p1; sp.p2 = (uint16_t*)b->p2;
-    sp.rates = b->rates; sp.integ = b->integ; sp.procstat = b->procstat; sp.sc = b->sc;
-    sp.R = b->R; sp.nsteps = n;
+    int rc = ensure_compact(b);
+    if (rc) return rc;
+    KbSmemParams sp = smem_params(b);
+    sp.nsteps = n;
     const int threads = b->wpc * 32;
     const int blocks = (b->R + b->wpc - 1) / b->wpc;
-    if (b->ppl == 2) {
-        CU(cudaFuncSetAttribute(kb_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
-        kb_smem_kernel<2><<<blocks, threads, b->smem_bytes, b->stream>>>(sp);
-    } else {
-        CU(cudaFuncSetAttribute(kb_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
-        kb_smem_kernel<1><<<blocks, threads, b->smem_bytes, b->stream>>>(sp);
+#define KB_LAUNCH(PPL, NC)                                                                                          \
+    do {                                                                                                            \
+        CU(cudaFuncSetAttribute(kb_smem_kernel<PPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes)); \
+        kb_smem_kernel<PPL, NC><<<blocks, threads, b->smem_bytes, b->stream>>>(sp);                                 \
+    } while (0)
+#define KB_LAUNCH_NC(PPL)                  \
+    switch (b->ncond) {                    \
+    case 0: KB_LAUNCH(PPL, 0); break;      \
+    case 1: KB_LAUNCH(PPL, 1); break;      \
+    case 2: KB_LAUNCH(PPL, 2); break;      \
+    case 3: KB_LAUNCH(PPL, 3); break;      \
+    default: KB_LAUNCH(PPL, 4); break;     \
     }
+    if (b->ppl == 2) { KB_LAUNCH_NC(2) } else { KB_LAUNCH_NC(1) }
+#undef KB_LAUNCH_NC
+#undef KB_LAUNCH
     CU(cudaGetLastError());
     return KMOS_B200_OK;
 }
@@ -627,7 +682,9 @@ extern "C" int kmos_b200_get_avail_sites(kmos_b200_batch* b, int32_t replica, in
     const int P = m.n_proc, C = b->g.ncells, V = b->g.volume, sp = m.spuck;
     std::vector<unsigned char> h1(b->plane_bytes), h2(b->plane_bytes);
     std::vector<int32_t> ns(P);
-    int rc = get_array(b, h1.data(), (const char*)b->p1 + (size_t)replica * b->plane_bytes, b->plane_bytes);
+    int rc = ensure_canonical(b);
+    if (rc) return rc;
+    rc = get_array(b, h1.data(), (const char*)b->p1 + (size_t)replica * b->plane_bytes, b->plane_bytes);
     if (!rc) rc = get_array(b, h2.data(), (const char*)b->p2 + (size_t)replica * b->plane_bytes, b->plane_bytes);
     if (!rc) rc = get_array(b, ns.data(), b->nsites + (size_t)replica * P, (size_t)P * 4);
     if (rc) return rc;

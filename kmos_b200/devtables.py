@@ -1,59 +1,62 @@
-"""Per-event lane tables for the shared-memory CUDA kernel (SEC_DEVICE of the model blob).
+"""Per-event lane tables for the shared-memory CUDA kernel (SEC_DEVICE of the model blob), version 2.
 
-The generated Fortran executes, for a chosen (process, site), a fixed *sequence* of put_/take_ routines
-(local_smart; kmos/io/__init__.py:305-465, 2219-2409).  Each routine is: one ``replace_species``, a flat
-list of guarded ``del_proc`` and an if-tree of ``get_species`` probes ending in ``add_proc`` leaves.
-Bit-exact parity only requires that, *per process*, the add/del calls hit ``avail_sites`` in the
-reference order (different processes own disjoint rows of ``avail_sites``/``nr_of_sites``;
-base.mpy:211-302).  So the whole event is flattened here, at export time, into
+1. Event flattening.  For a chosen (process, site) the generated Fortran executes a fixed *sequence* of
+put_/take_ routines (local_smart; kmos/io/__init__.py:305-465, 2219-2409), each one ``replace_species``,
+a flat list of guarded ``del_proc`` and an if-tree of ``get_species`` probes ending in ``add_proc``
+leaves.  The whole event is flattened at export time into
 
-    writes   the replace_species calls (site offset, old, new), in order
+    writes   the replace_species calls (site, old, new), in order
     ops      every del/add candidate of every action, in textual (= execution) order:
-             DEL_IF (q, anchor)            -- guard avail_sites(q, anchor, 2) /= 0 read at execution time
-             ADD    (q, anchor, conds...)  -- leaf of the if-tree; conds = species tests on the path
+             DEL_IF (q, anchor)            guard avail_sites(q, anchor, 2) /= 0, read at execution time
+             ADD    (q, anchor, conds...)  leaf of the if-tree; conds = species tests on its path
 
-and then scheduled into *rounds*: within a round every op touches a different process, so the 32 lanes
-of the replica's warp execute a round concurrently; ops of the same process land in successive rounds in
-their original order.
+While an event runs, the species on its own action sites are known at compile time (its conditions fix
+them before, its actions after), so if-tree probes of those sites are folded here: ops that cannot fire
+are dropped and the remaining probes only touch sites the event does not modify -- every lane can
+evaluate them up front, independent of the order of the event's own writes.
 
-Static resolution: while an event runs, the species on its own action sites are known at compile time
-(the event's conditions fix them before, its actions after), so every if-tree probe of such a site is
-folded here -- ops that cannot fire are dropped, the rest only probe sites the event does not modify.
-Lattice probes are therefore independent of the order of the event's own writes and all lanes can
-evaluate them up front.
+2. Compact avail-site storage.  The reference keeps avail_sites(nr_of_proc, volume, 2) (base.mpy:88).
+Two processes registered on the same site type whose conditions contradict each other on some site can
+never be available on the same cell at the same time, so
+    * plane 2 (site -> position) is stored per *exclusivity class* (a clique of such processes) and cell:
+      one uint16 entry (member << POS_BITS | position), instead of one entry per process and cell;
+    * plane 1 (position -> site) is stored per *arena*: two processes of one class share ncells entries,
+      one list growing from the left, the other from the right (their lengths can never sum above ncells).
+For the RuO2 model this is 36x400x2x2 B = 57.6 KB -> ~19 KB per replica, i.e. 3x more replicas per SM.
+The order of every process' list -- all that determine_procsite can observe -- is unchanged.
 
-Layout of the int32 section (all offsets relative to the section start):
-    [0] version  [1] supported  [2] n_events  [3] events_off  [4] ops_off  [5] n_ops
-    [6] anchors_off [7] n_anchors  [8] conds_off  [9] n_conds  [10] max_rounds  [11] max_ops_per_event
-    [12] proc_anchor_off (n_proc words: 1-based site type each process is registered on)
-    events: EVENT_STRIDE words each:
-        [0] ops_start [1] n_rounds [2] n_writes [3] base site type
-        [4..4+MAX_ROUNDS)  cumulative op count at the end of each round
-        then MAX_WRITES x (packed offset, old | new<<8)
-    ops: 2 words:  w0 = kind | q<<4 | anchor_idx<<16 | ncond<<24 ;  w1 = 4 x u8 cond indices
-    anchors / cond sites: 1 word: (dx&255) | (dy&255)<<8 | (dz&255)<<16 | n<<24   (n = absolute site type)
-    conds: 2 words: packed site, species mask
+3. Rounds.  Bit-exact parity needs the add/del calls to hit each list in the reference order, nothing
+more.  Ops are list-scheduled into rounds such that two ops sharing a resource (an arena, or a class
+entry of the same anchor cell) keep their textual order in successive rounds; the ops of one round touch
+disjoint memory and run one per lane.
+
+Section layout (int32 words, offsets relative to the section start):
+    [0] version=2 [1] supported [2] n_events [3] events_off [4] ops_off [5] n_ops [6] op_stride
+    [7] offsets_off [8] n_offsets [9] procinfo_off [10] n_classes [11] n_arenas [12] max_rounds
+    [13] max_ops_per_event [14] max_ncond [15] reserved
+    events   EVENT_WORDS each: w0 = ops_start | n_rounds<<16 | n_writes<<20 | min_q<<24
+                               w1,w2 = cumulative op count after each round (8 x u8), w3 = 0
+                               w4..w7 = writes: off_id | n<<5 | old<<8 | new<<12
+    ops      op_stride words each: header = kind | ncond<<1 | off_id<<4 | q<<9 | cls<<15 | member<<20 |
+                               arena<<23 | dir<<29 ; then ncond words off_id | n<<5 | mask<<8
+    offsets  1 word each: (dx&255) | (dy&255)<<8 | (dz&255)<<16
+    procinfo 1 word per process: arena | dir<<6 | cls<<7 | member<<12 | anchor_n<<15
 """
+EVENT_WORDS = 8
 MAX_ROUNDS = 8
 MAX_WRITES = 4
-EVENT_STRIDE = 4 + MAX_ROUNDS + 2 * MAX_WRITES
-KIND_NOP, KIND_DEL_IF, KIND_ADD = 0, 1, 2
-DEV_VERSION = 1
+MAX_COND = 4
+MAX_OFFSETS = 32
+MAX_CLASS_MEMBERS = 7
+POS_BITS = 13
+KIND_DEL_IF, KIND_ADD = 0, 1
+DEV_VERSION = 2
 WARP = 32
+HEADER_WORDS = 16
 
 
 class Unsupported(Exception):
     pass
-
-
-def pack_site(off):
-    dx, dy, dz, n = off
-    for d in (dx, dy, dz):
-        if not -128 <= d <= 127:
-            raise Unsupported("offset out of byte range")
-    if not 0 < n < 128:
-        raise Unsupported("site type out of range")
-    return (dx & 255) | ((dy & 255) << 8) | ((dz & 255) << 16) | (n << 24)
 
 
 def _add4(a, b):
@@ -63,18 +66,17 @@ def _add4(a, b):
 def flatten_event(ir, proc_index):
     """-> (base_n, writes, ops) for process `proc_index` (0-based) of a local_smart model.
 
-    writes: [(off4_abs, old, new)]; ops: [(kind, q, anchor_off4_abs, [(off4_abs, mask)...])].
+    writes: [(off4_abs, old, new)]; ops: [(kind, q, anchor_off4_abs, [(off4_abs, mask)...], group)] with
+    group = 2*action (the action's guarded dels) or 2*action+1 (its if-tree adds).
     Offsets are relative to the selected site's cell, 4th component = absolute site type.
     """
     calls = ir["run_proc"][proc_index]
     rsite = ir["routine_site"]
     all_mask = (1 << len(ir["species"])) - 1
-    # site type of the event's base coordinate: routine's site type minus the call's dn
     first = calls[0]
     base_n = rsite[first[1]] - first[2][3]
-    # species known on the event's own sites: before the first write = that write's `old`
     known = {}
-    seq = []  # (routine stmts, abs offset of routine base)
+    seq = []
     for _c, rname, off in calls:
         rb = [off[0], off[1], off[2], base_n + off[3]]
         if rb[3] != rsite[rname]:
@@ -83,9 +85,9 @@ def flatten_event(ir, proc_index):
     for stmts, rb in seq:
         for st in stmts:
             if st[0] == "replace":
-                key = tuple(_add4(rb, st[1]))
-                known.setdefault(key, st[2])
+                known.setdefault(tuple(_add4(rb, st[1])), st[2])
     writes, ops = [], []
+    action = [0]
 
     def walk(block, rb, conds):
         for st in block:
@@ -102,11 +104,11 @@ def flatten_event(ir, proc_index):
                     raise Unsupported("if_can body is not the matching del_proc")
                 if conds:
                     raise Unsupported("guarded del inside a select")
-                ops.append((KIND_DEL_IF, st[1], _add4(rb, st[2]), []))
+                ops.append((KIND_DEL_IF, st[1], _add4(rb, st[2]), [], 2 * action[0]))
             elif k == "add":
                 if isinstance(st[1], list) or st[3] is not None:
                     raise Unsupported("nli/otf add in local_smart table")
-                ops.append((KIND_ADD, st[1], _add4(rb, st[2]), list(conds)))
+                ops.append((KIND_ADD, st[1], _add4(rb, st[2]), list(conds), 2 * action[0] + 1))
             elif k == "select":
                 site = _add4(rb, st[1])
                 seen_mask = 0
@@ -131,17 +133,94 @@ def flatten_event(ir, proc_index):
 
     for stmts, rb in seq:
         walk(stmts, rb, [])
+        action[0] += 1
     return base_n, writes, ops
 
 
-def schedule_rounds(ops, resource_of=None):
-    """Greedy list scheduling: ops of one process keep their order in successive rounds, a round holds at
-    most WARP ops.  Returns list of rounds (lists of op indices)."""
+def process_conditions(ir):
+    """Full condition list of every process relative to its anchor site, read off the touchup if-trees
+    (kmos/io/__init__.py:2411-2443): {q: [(off4_rel, mask), ...]} with off4_rel[3] = absolute site type."""
+    rsite = ir["routine_site"]
+    all_mask = (1 << len(ir["species"])) - 1
+    out = {}
+
+    def walk(block, base_n, conds):
+        for st in block:
+            if st[0] == "add" and not isinstance(st[1], list):
+                a = st[2]
+                rel = [([c[0][0] - a[0], c[0][1] - a[1], c[0][2] - a[2], c[0][3]], c[1]) for c in conds]
+                if st[1] in out and sorted(map(repr, out[st[1]])) != sorted(map(repr, rel)):
+                    raise Unsupported("process %d has two different condition sets" % st[1])
+                out[st[1]] = rel
+            elif st[0] == "select":
+                site = [st[1][0], st[1][1], st[1][2], base_n + st[1][3]]
+                seen = 0
+                for key, body in st[2]:
+                    mask = (all_mask & ~seen) if key is None else (sum(1 << s for s in set(key)) & ~seen)
+                    seen |= mask
+                    walk(body, base_n, conds + [(site, mask)])
+    for name, stmts in ir["routines"].items():
+        if name.lower().startswith("touchup_") and name in rsite:
+            walk(stmts, rsite[name], [])
+    return out
+
+
+def exclusive(ca, cb):
+    """True if two condition lists (same anchor type) contradict each other on some site."""
+    for sa, ma in ca:
+        for sb, mb in cb:
+            if sa == sb and (ma & mb) == 0:
+                return True
+    return False
+
+
+def exclusivity_classes(ir, proc_anchor):
+    """Greedy clique cover of the `mutually exclusive` relation -> (classes, cls_of, member_of)."""
+    nproc = len(ir["procs"])
+    conds = process_conditions(ir)
+    classes = []
+    for q in range(1, nproc + 1):
+        placed = False
+        if q in conds:
+            for cl in classes:
+                if len(cl) < MAX_CLASS_MEMBERS and proc_anchor[cl[0] - 1] == proc_anchor[q - 1] and \
+                        all(c in conds and exclusive(conds[q], conds[c]) for c in cl):
+                    cl.append(q)
+                    placed = True
+                    break
+        if not placed:
+            classes.append([q])
+    cls_of, member_of = {}, {}
+    for ci, cl in enumerate(classes):
+        for mi, q in enumerate(cl):
+            cls_of[q] = ci
+            member_of[q] = mi + 1
+    return classes, cls_of, member_of
+
+
+def schedule_rounds(ops, lists_of, entry_of):
+    """List scheduling into rounds of at most WARP ops (one op per lane, rounds separated by __syncwarp).
+
+    Ordering that must be kept from the reference's textual order:
+      * ops on the same process list (``lists_of(op)``: its nr_of_sites counter and list) -- always;
+      * ops on the same class entry (``entry_of(op)``: exclusivity class x anchor cell) -- only across
+        *groups*.  A group is the guarded-del block or the if-tree add block of one action; within a
+        group at most one op can fire on a given entry (one member of an exclusivity class is registered
+        on a cell / can become available on it), so its ops need no mutual order.
+    """
     rounds = []
-    last_round = {}
+    last_list = {}
+    entry_groups = {}  # entry -> {group: last round}
     for i, op in enumerate(ops):
-        res = op[1] if resource_of is None else resource_of[op[1]]
-        r = last_round.get(res, -1) + 1
+        group = op[4]
+        r = -1
+        for x in lists_of(op):
+            r = max(r, last_list.get(x, -1))
+        eg = entry_groups.setdefault(entry_of(op), {})
+        for g, rr in eg.items():
+            if g != group:
+                r = max(r, rr)
+        r += 1
         while True:
             if r == len(rounds):
                 rounds.append([])
@@ -149,80 +228,120 @@ def schedule_rounds(ops, resource_of=None):
                 break
             r += 1
         rounds[r].append(i)
-        last_round[res] = r
+        for x in lists_of(op):
+            last_list[x] = r
+        eg[group] = max(eg.get(group, -1), r)
     return rounds
 
 
 def compile_device_tables(ir, asm=None):
     info = {"supported": False}
     nproc = len(ir["procs"])
-    header = [DEV_VERSION, 0] + [0] * 11
+    header = [DEV_VERSION, 0] + [0] * (HEADER_WORDS - 2)
     if ir["backend"] != "local_smart":
         info["reason"] = "shared-memory tables are generated for local_smart only"
         return header, info
     try:
-        from .tables import proc_site_masks
-        masks = proc_site_masks(ir)
-        proc_anchor = []
-        for m in masks:
-            if m == 0 or (m & (m - 1)):
-                raise Unsupported("process registered on %s site types" % bin(m).count("1"))
-            proc_anchor.append(m.bit_length())
+        from .tables import proc_anchor_types
+        proc_anchor = proc_anchor_types(ir)
+        if any(a == 0 for a in proc_anchor):
+            raise Unsupported("a process is registered on several site types")
         if nproc > 64:
             raise Unsupported("more than 64 processes")
         if len(ir["species"]) > 16:
             raise Unsupported("more than 16 species")
-        anchors, conds = {}, {}
-        ops_words, events_words = [], []
-        stats = []
-        max_rounds = max_ops = 0
+        if ir["spuck"] > 7:
+            raise Unsupported("more than 7 sites per cell")
+        classes, cls_of, member_of = exclusivity_classes(ir, proc_anchor)
+        if len(classes) > 32:
+            raise Unsupported("more than 32 exclusivity classes")
+        # arenas: consecutive members of a class share one (left list, right list)
+        arena_of, dir_of = {}, {}
+        n_arenas = 0
+        for cl in classes:
+            for i in range(0, len(cl), 2):
+                arena_of[cl[i]], dir_of[cl[i]] = n_arenas, 0
+                if i + 1 < len(cl):
+                    arena_of[cl[i + 1]], dir_of[cl[i + 1]] = n_arenas, 1
+                n_arenas += 1
+        if n_arenas > 64:
+            raise Unsupported("more than 64 arenas")
+
+        offsets = {}
+
+        def off_id(o):
+            key = (o[0], o[1], o[2])
+            for d in key:
+                if not -128 <= d <= 127:
+                    raise Unsupported("offset out of byte range")
+            if key not in offsets:
+                if len(offsets) == MAX_OFFSETS:
+                    raise Unsupported("more than %d distinct neighbour offsets" % MAX_OFFSETS)
+                offsets[key] = len(offsets)
+            return offsets[key]
+
+        off_id([0, 0, 0])
+        flat = []
+        max_ncond = 0
         for p in range(nproc):
             base_n, writes, ops = flatten_event(ir, p)
             if base_n != proc_anchor[p]:
                 raise Unsupported("process %d is selected on site type %d but registered on %d"
                                   % (p + 1, base_n, proc_anchor[p]))
-            for _k, q, aoff, _c in ops:
+            for _k, q, aoff, cs, _g in ops:
                 if aoff[3] != proc_anchor[q - 1]:
                     raise Unsupported("anchor site type mismatch")
-            rounds = schedule_rounds(ops)
-            if len(rounds) > MAX_ROUNDS:
-                raise Unsupported("event needs %d rounds" % len(rounds))
+                max_ncond = max(max_ncond, len(cs))
             if len(writes) > MAX_WRITES:
                 raise Unsupported("event writes %d sites" % len(writes))
-            ops_start = len(ops_words) // 2
-            cum = []
-            n = 0
+            flat.append((base_n, writes, ops))
+        if max_ncond > MAX_COND:
+            raise Unsupported("add with %d dynamic conditions" % max_ncond)
+        op_stride = 1 + max_ncond
+
+        ops_words, events_words, stats = [], [], []
+        max_rounds = max_ops = 0
+        for p, (base_n, writes, ops) in enumerate(flat):
+            rounds = schedule_rounds(ops, lambda op: [op[1]],
+                                     lambda op: (cls_of[op[1]], op[2][0], op[2][1], op[2][2]))
+            if len(rounds) > MAX_ROUNDS:
+                raise Unsupported("event needs %d rounds" % len(rounds))
+            ops_start = len(ops_words) // op_stride
+            if ops_start >= 1 << 16:
+                raise Unsupported("too many ops")
+            cum, n = [], 0
             for rnd in rounds:
                 for i in rnd:
-                    kind, q, aoff, cs = ops[i]
-                    if len(cs) > 4:
-                        raise Unsupported("add with %d dynamic conditions" % len(cs))
-                    a_idx = anchors.setdefault(pack_site(aoff), len(anchors))
-                    c_idx = [conds.setdefault((pack_site(s), m), len(conds)) for s, m in cs]
-                    if a_idx > 255 or any(c > 254 for c in c_idx):
-                        raise Unsupported("pool overflow")
-                    w1 = 0
-                    for j, c in enumerate(c_idx):
-                        w1 |= c << (8 * j)
-                    ops_words += [kind | (q << 4) | (a_idx << 16) | (len(cs) << 24), w1]
+                    kind, q, aoff, cs, _g = ops[i]
+                    hdr = (kind | (len(cs) << 1) | (off_id(aoff) << 4) | ((q - 1) << 9) | (cls_of[q] << 15) |
+                           (member_of[q] << 20) | (arena_of[q] << 23) | (dir_of[q] << 29))
+                    words = [hdr]
+                    for s, m in cs:
+                        words.append(off_id(s) | (s[3] << 5) | (m << 8))
+                    words += [0] * (op_stride - len(words))
+                    ops_words += words
                 n += len(rnd)
+                if n > 255:
+                    raise Unsupported("more than 255 ops in one event")
                 cum.append(n)
             cum += [n] * (MAX_ROUNDS - len(cum))
-            ev = [ops_start, len(rounds), len(writes), base_n] + cum
+            min_q = min([q for _k, q, _a, _c, _g in ops] + [nproc]) - 1
+            w0 = ops_start | (len(rounds) << 16) | (len(writes) << 20) | (min_q << 24)
+            w1 = cum[0] | (cum[1] << 8) | (cum[2] << 16) | (cum[3] << 24)
+            w2 = cum[4] | (cum[5] << 8) | (cum[6] << 16) | (cum[7] << 24)
+            ev = [w0, w1, w2, 0]
             for off, old, new in writes:
-                ev += [pack_site(off), old | (new << 8)]
-            ev += [0, 0] * (MAX_WRITES - len(writes))
+                ev.append(off_id(off) | (off[3] << 5) | (old << 8) | (new << 12))
+            ev += [0] * (EVENT_WORDS - len(ev))
             events_words += ev
             max_rounds = max(max_rounds, len(rounds))
             max_ops = max(max_ops, len(ops))
             stats.append((len(ops), len(rounds), len(writes)))
-        anchors_words = [0] * len(anchors)
-        for packed, i in anchors.items():
-            anchors_words[i] = packed
-        conds_words = [0] * (2 * len(conds))
-        for (packed, m), i in conds.items():
-            conds_words[2 * i] = packed
-            conds_words[2 * i + 1] = m
+        offsets_words = [0] * len(offsets)
+        for (dx, dy, dz), i in offsets.items():
+            offsets_words[i] = (dx & 255) | ((dy & 255) << 8) | ((dz & 255) << 16)
+        procinfo = [arena_of[q] | (dir_of[q] << 6) | (cls_of[q] << 7) | (member_of[q] << 12) |
+                    (proc_anchor[q - 1] << 15) for q in range(1, nproc + 1)]
     except Unsupported as e:
         info["reason"] = str(e)
         return header, info
@@ -230,16 +349,15 @@ def compile_device_tables(ir, asm=None):
     def s32(w):
         return w - (1 << 32) if w >= (1 << 31) else w
 
-    hdr_len = 13
-    events_off = hdr_len
+    events_off = HEADER_WORDS
     ops_off = events_off + len(events_words)
-    anchors_off = ops_off + len(ops_words)
-    conds_off = anchors_off + len(anchors_words)
-    pa_off = conds_off + len(conds_words)
-    header = [DEV_VERSION, 1, nproc, events_off, ops_off, len(ops_words) // 2, anchors_off, len(anchors_words),
-              conds_off, len(conds_words) // 2, max_rounds, max_ops, pa_off]
-    words = header + events_words + ops_words + anchors_words + conds_words + proc_anchor
-    info.update({"supported": True, "n_ops": len(ops_words) // 2, "n_anchors": len(anchors_words),
-                 "n_conds": len(conds_words) // 2, "max_rounds": max_rounds, "max_ops": max_ops,
+    offsets_off = ops_off + len(ops_words)
+    procinfo_off = offsets_off + len(offsets_words)
+    header = [DEV_VERSION, 1, nproc, events_off, ops_off, len(ops_words) // op_stride, op_stride, offsets_off,
+              len(offsets_words), procinfo_off, len(classes), n_arenas, max_rounds, max_ops, max_ncond, 0]
+    words = header + events_words + ops_words + offsets_words + procinfo
+    info.update({"supported": True, "n_ops": len(ops_words) // op_stride, "op_stride": op_stride,
+                 "n_offsets": len(offsets_words), "n_classes": len(classes), "n_arenas": n_arenas,
+                 "classes": classes, "max_rounds": max_rounds, "max_ops": max_ops, "max_ncond": max_ncond,
                  "per_event": stats, "bytes": 4 * len(words), "proc_anchor": proc_anchor})
     return [s32(w) for w in words], info

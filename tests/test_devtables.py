@@ -13,14 +13,16 @@ from kmos_b200 import devtables as dt
 from oracle import oracle
 
 
-def _unpack(w):
-    def s8(b):
-        return b - 256 if b >= 128 else b
-    return s8(w & 255), s8((w >> 8) & 255), s8((w >> 16) & 255), (w >> 24) & 255
+def _s8(b):
+    return b - 256 if b >= 128 else b
 
 
 class EventModel(object):
-    def __init__(self, blob, info, o):
+    """Python model of the kernel's compact storage and event phase (kb_smem.cuh).  The ops of one round
+    run concurrently on the GPU, so here they are executed in a random order: the result must not depend
+    on it."""
+
+    def __init__(self, blob, info, o, spare=None):
         from kmos_b200.tables import SEC_DEVICE
         nsec = blob[13]
         for i in range(nsec):
@@ -28,82 +30,110 @@ class EventModel(object):
                 off, ln = blob[14 + 3 * i + 1], blob[14 + 3 * i + 2]
         self.d = [int(x) & 0xFFFFFFFF for x in blob[off:off + ln]]
         d = self.d
-        assert d[1] == 1
-        self.events_off, self.ops_off, self.anchors_off, self.conds_off = d[3], d[4], d[6], d[8]
+        assert d[0] == dt.DEV_VERSION and d[1] == 1
+        self.events_off, self.ops_off, self.stride = d[3], d[4], d[6]
+        self.offsets = [(_s8(w & 255), _s8((w >> 8) & 255), _s8((w >> 16) & 255)) for w in d[d[7]:d[7] + d[8]]]
+        self.procinfo = d[d[9]:d[9] + d[2]]
+        self.n_classes, self.n_arenas = d[10], d[11]
         self.size = o.size
         self.spuck = o.spuck
         self.P = o.n_proc
+        self.C = o.volume // o.spuck
+        self.cap = self.C + (d[13] if spare is None else spare)
+        self.rng = np.random.RandomState(5)
         self.lattice = o.lattice.copy()
+        self.n = [int(x) for x in o.nr_of_sites]
+        self.p1 = [None] * (self.n_arenas * self.cap)
+        self.p2 = [0] * (self.n_classes * self.C)
         av = o.avail_sites
-        self.n = o.nr_of_sites.copy()
-        self.p1 = [list(av[q, :self.n[q], 0]) for q in range(self.P)]
-        self.p2 = [dict((s, k + 1) for k, s in enumerate(self.p1[q])) for q in range(self.P)]
+        for q in range(self.P):
+            arena, dirn, cls, member, an = self.pinfo(q)
+            for k in range(self.n[q]):
+                cell = (int(av[q, k, 0]) - 1) // self.spuck
+                assert (int(av[q, k, 0]) - 1) % self.spuck + 1 == an
+                self.p1[self.slot(arena, dirn, k)] = cell
+                assert self.p2[cls * self.C + cell] == 0, "two members of a class on one cell"
+                self.p2[cls * self.C + cell] = (member << dt.POS_BITS) | (k + 1)
 
-    def nr(self, x, y, z, n):
+    def pinfo(self, q):
+        w = self.procinfo[q]
+        return w & 63, (w >> 6) & 1, (w >> 7) & 31, (w >> 12) & 7, (w >> 15) & 7
+
+    def slot(self, arena, dirn, k):
+        return arena * self.cap + (self.cap - 1 - k if dirn else k)
+
+    def cell(self, x, y, z):
         L = self.size
-        return self.spuck * ((x % L[0]) + L[0] * ((y % L[1]) + L[1] * (z % L[2]))) + n
+        return (x % L[0]) + L[0] * ((y % L[1]) + L[1] * (z % L[2]))
 
     def run(self, proc, site):
         d = self.d
         c = (site - 1) // self.spuck
         x, y, z = c % self.size[0], (c // self.size[0]) % self.size[1], c // (self.size[0] * self.size[1])
-        ev = self.events_off + (proc - 1) * dt.EVENT_STRIDE
-        ops_start, n_rounds, n_writes, base_n = d[ev:ev + 4]
-        assert base_n == (site - 1) % self.spuck + 1
-        cum = d[ev + 4:ev + 4 + dt.MAX_ROUNDS]
-        # lattice probes are taken BEFORE the writes here and must give the same answer as after
+        nb = [self.cell(x + o[0], y + o[1], z + o[2]) for o in self.offsets]
+        ev = self.events_off + (proc - 1) * dt.EVENT_WORDS
+        w0, w1, w2 = d[ev], d[ev + 1], d[ev + 2]
+        ops_start, n_rounds, n_writes = w0 & 0xFFFF, (w0 >> 16) & 15, (w0 >> 20) & 15
+        ends = w1 | (w2 << 32)
         pre = self.lattice.copy()
         for w in range(n_writes):
-            dx, dy, dz, n = _unpack(d[ev + 4 + dt.MAX_ROUNDS + 2 * w])
-            oldnew = d[ev + 4 + dt.MAX_ROUNDS + 2 * w + 1]
-            s = self.nr(x + dx, y + dy, z + dz, n)
-            assert self.lattice[s - 1] == (oldnew & 255)
-            self.lattice[s - 1] = oldnew >> 8
+            ww = d[ev + 4 + w]
+            idx = nb[ww & 31] * self.spuck + ((ww >> 5) & 7) - 1
+            assert self.lattice[idx] == (ww >> 8) & 15
+            self.lattice[idx] = (ww >> 12) & 15
         start = 0
         for r in range(n_rounds):
-            touched = set()
-            for i in range(start, cum[r]):
-                w0, w1 = d[self.ops_off + 2 * (ops_start + i)], d[self.ops_off + 2 * (ops_start + i) + 1]
-                kind, q, a_idx, ncond = w0 & 15, (w0 >> 4) & 0xFFF, (w0 >> 16) & 255, w0 >> 24
-                assert q not in touched, "two ops of one process in the same round"
-                touched.add(q)
-                dx, dy, dz, n = _unpack(d[self.anchors_off + a_idx])
-                a = self.nr(x + dx, y + dy, z + dz, n)
+            endr = (ends >> (8 * r)) & 255
+            assert endr - start <= 32
+            order = list(range(start, endr))
+            self.rng.shuffle(order)
+            for i in order:
+                base = self.ops_off + (ops_start + i) * self.stride
+                h = d[base]
+                kind, ncond, ca = h & 1, (h >> 1) & 7, nb[(h >> 4) & 31]
+                q, cls, member = (h >> 9) & 63, (h >> 15) & 31, (h >> 20) & 7
+                arena, dirn = (h >> 23) & 63, (h >> 29) & 1
+                assert (arena, dirn, cls, member) == self.pinfo(q)[:4]
                 if kind == dt.KIND_ADD:
                     ok = True
                     for j in range(ncond):
-                        ci = (w1 >> (8 * j)) & 255
-                        cx, cy, cz, cn = _unpack(d[self.conds_off + 2 * ci])
-                        mask = d[self.conds_off + 2 * ci + 1]
-                        cs = self.nr(x + cx, y + cy, z + cz, cn)
-                        assert pre[cs - 1] == self.lattice[cs - 1], "probe of a site the event writes"
-                        ok = ok and ((mask >> self.lattice[cs - 1]) & 1)
+                        cw = d[base + 1 + j]
+                        idx = nb[cw & 31] * self.spuck + ((cw >> 5) & 7) - 1
+                        assert pre[idx] == self.lattice[idx], "probe of a site the event writes"
+                        ok = ok and (((cw >> 8) >> self.lattice[idx]) & 1)
                     if ok:
-                        assert a not in self.p2[q - 1]
-                        self.p1[q - 1].append(a)
-                        self.p2[q - 1][a] = len(self.p1[q - 1])
-                elif kind == dt.KIND_DEL_IF:
-                    pos = self.p2[q - 1].get(a, 0)
-                    if pos:
-                        lst = self.p1[q - 1]
-                        last = lst[-1]
-                        if pos < len(lst):
-                            lst[pos - 1] = last
-                            self.p2[q - 1][last] = pos
-                        lst.pop()
-                        del self.p2[q - 1][a]
-            start = cum[r]
+                        assert self.p2[cls * self.C + ca] == 0, "class entry occupied"
+                        s = self.slot(arena, dirn, self.n[q])
+                        self.p1[s] = ca
+                        self.p2[cls * self.C + ca] = (member << dt.POS_BITS) | (self.n[q] + 1)
+                        self.n[q] += 1
+                else:
+                    e = self.p2[cls * self.C + ca]
+                    if (e >> dt.POS_BITS) == member:
+                        pos = e & ((1 << dt.POS_BITS) - 1)
+                        nq = self.n[q]
+                        last = self.p1[self.slot(arena, dirn, nq - 1)]
+                        if pos < nq:
+                            self.p1[self.slot(arena, dirn, pos - 1)] = last
+                            self.p2[cls * self.C + last] = (member << dt.POS_BITS) | pos
+                        self.p1[self.slot(arena, dirn, nq - 1)] = None
+                        self.p2[cls * self.C + ca] = 0
+                        self.n[q] = nq - 1
+            start = endr
 
     def check(self, o):
         assert np.array_equal(self.lattice, o.lattice)
         n = o.nr_of_sites
         av = o.avail_sites
+        assert list(n) == self.n
         for q in range(self.P):
-            assert len(self.p1[q]) == n[q]
-            assert self.p1[q] == list(av[q, :n[q], 0]), "avail_sites order differs for process %d" % (q + 1)
-            for s, k in self.p2[q].items():
-                assert av[q, s - 1, 1] == k
-            assert np.count_nonzero(av[q, :, 1]) == n[q]
+            arena, dirn, cls, member, an = self.pinfo(q)
+            mine = [self.p1[self.slot(arena, dirn, k)] * self.spuck + an for k in range(self.n[q])]
+            assert mine == list(av[q, :n[q], 0]), "avail_sites order differs for process %d" % (q + 1)
+            for k, s in enumerate(mine):
+                assert self.p2[cls * self.C + (s - 1) // self.spuck] == (member << dt.POS_BITS) | (k + 1)
+        # every non-empty class entry belongs to exactly one registered (process, cell)
+        assert sum(1 for e in self.p2 if e) == sum(self.n)
 
 
 @pytest.mark.parametrize("name,size,steps", [
@@ -111,6 +141,7 @@ class EventModel(object):
     ("mini_101_local_smart", [5, 4], 300),
     ("zgb_local_smart", [12, 10], 3000),
     ("ruo2_local_smart", [6, 5], 4000),
+    ("mini_101_local_smart", [3, 3], 2000),
     ("ruo2_local_smart", [20, 20], 1500),
     ("pairwise_local_smart", [8, 8], 2000),
 ])
