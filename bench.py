@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- aggregate kMC steps/s of the step-loop engine on the BASELINE headline workload.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): CO oxidation on RuO2(110)
+(reference: examples/render_co_oxidation_ruo2.py), 20x20 unit cells, 16384 replicas PER GPU = 16 T x 16 p_CO
+grid points x 64 seeds, local_smart rule tables, default-species initial state.  A bench "step" is one
+`do_kmc_steps(inner)` over the whole batch followed by the tally reduction of one sampling point (per-GPU
+reduce kernel + NCCL all-reduce when N > 1).  Weak scaling: every rank owns its own 16384 replicas; there is
+no inter-GPU traffic during stepping.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--inner n] [--impl ours|reference]
+
+N > 1 is launched by the driver through torch.distributed.run (one rank per GPU, NCCL).
+`--impl reference` times the reference semantics on the host cores (the CPU oracle port: the reference is
+Fortran and this image has no Fortran compiler), process pool over all cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "aggregate kMC steps/s over replicas, RuO2 CO-ox 20x20"
+UNIT = "kMC steps/s"
+MODEL = "ruo2_local_smart"
+SIZE = [20, 20]
+REPLICAS_PER_GPU = 16384
+N_T, N_P, SEEDS = 16, 16, 64
+
+
+def load_workload():
+    from kmos_b200 import tables, workloads
+    ir = tables.load_ir(os.path.join(REPO, "tests", "golden", "models", MODEL + ".json"))
+    blob, info = tables.build_blob(ir)
+    rates, group_of, grid = workloads.ruo2_grid(ir, n_T=N_T, n_p=N_P, seeds=SEEDS)
+    assert rates.shape[0] == REPLICAS_PER_GPU
+    return ir, blob, info, rates, group_of, grid
+
+
+def algorithmic_bytes_per_step(P, c):
+    """bytes the reference's data structures move per kMC step at reference widths.
+    c = per-step averages of the oracle's event counters on this workload."""
+    log2p = int(np.ceil(np.log2(P)))
+    return (20 * P + 48 + 28 * P + 8 * (log2p + 3) + 8 + 32 + 12 * c["n_rs"] + 8 * c["n_chk"]
+            + 36 * c["n_del"] + 8 * c["n_gs"] + 20 * c["n_add"])
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference semantics (oracle port) on all host cores, ModelRunner-style process pool
+# (kmos/run/__init__.py:2330-2366): replicas dealt round-robin, each worker runs its replicas in turn.
+# --------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    blob, rates, seeds, ids, warm, n = args
+    from oracle import oracle
+    t_total = 0.0
+    counters = np.zeros(5)
+    steps = 0
+    for r, seed, rid in zip(rates, seeds, ids):
+        o = oracle.Oracle(blob, SIZE, seed=int(seed), replica=int(rid), rates=r)
+        o.do_steps(warm)
+        o.reset_counters()
+        t0 = time.perf_counter()
+        st = o.do_steps(n)
+        t_total += time.perf_counter() - t0
+        assert st == 0
+        c = o.counters
+        counters += [c["n_rs"], c["n_chk"], c["n_del"], c["n_gs"], c["n_add"]]
+        steps += n
+    return t_total, steps, counters
+
+
+def cpu_pool_run(blob, rates, n_replicas, warm, n, cores, id_offset=0):
+    """-> (aggregate steps/s, per-step counter averages, wall seconds of the slowest worker)"""
+    import multiprocessing as mp
+    pick = np.linspace(0, rates.shape[0] - 1, n_replicas).astype(int)  # spread over the (T, p) grid
+    jobs = [[] for _ in range(cores)]
+    for i, r in enumerate(pick):
+        jobs[i % cores].append(r)
+    args = [(blob, rates[j], [1000 + x for x in j], [id_offset + x for x in j], warm, n) for j in jobs if j]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(args)) as pool:
+        out = pool.map(_cpu_worker, args)
+    slowest = max(o[0] for o in out)
+    steps = sum(o[1] for o in out)
+    cnt = sum(o[2] for o in out) / steps
+    counters = dict(zip(("n_rs", "n_chk", "n_del", "n_gs", "n_add"), cnt.tolist()))
+    return steps / slowest, counters, slowest
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    ir, blob, info, rates, group_of, grid = load_workload()
+    cores = host_cores()
+    n_rep = 2 * cores
+    warm, n = 20000, args.cpu_steps
+    # untimed warm-up steps, then K timed steps; each step = the bounded sample below
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, _c, wall = cpu_pool_run(blob, rates, n_rep, warm, n, cores)
+        if i >= args.warmup:
+            vals.append((v, wall))
+    value = float(np.mean([v for v, _ in vals]))
+    sample = "%d replicas spread over the T x p_CO grid x %d steps each (after %d warm-up steps), %d workers" % (
+        n_rep, n, warm, cores)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean([w for _, w in vals]) * 1e3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "impl": "reference",
+        "config": workload_config(grid, args, extra={"note": "reference semantics on host cores (CPU port of "
+                                                    "the generated Fortran; no Fortran compiler in this image)"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(grid, args, extra=None):
+    cfg = {"workload": "RuO2(110) CO oxidation 20x20 (examples/render_co_oxidation_ruo2.py), local_smart, "
+                       "%d replicas/GPU = %d T x %d p_CO x %d seeds" % (REPLICAS_PER_GPU, N_T, N_P, SEEDS),
+           "replicas_per_gpu": REPLICAS_PER_GPU, "lattice": SIZE, "processes": 36,
+           "kmc_steps_per_replica_per_step": args.inner,
+           "T_K": [grid["T"][0], grid["T"][-1]], "p_CO_bar": [grid["p_COgas"][0], grid["p_COgas"][-1]],
+           "p_O2_bar": grid["p_O2gas"], "rng": "Philox4x32-10 per replica",
+           "parallelism": "replica-sharded, %d GPU(s), NCCL tally all-reduce per step" % args.gpus}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def run_ours(args, rank, world, local_rank):
+    ir, blob, info, rates, group_of, grid = load_workload()
+    P = len(ir["procs"])
+
+    # ---- CPU baseline first (before CUDA is initialised in this process: the pool forks) ----------------
+    cpu = None
+    counters = None
+    if rank == 0:
+        cores = host_cores()
+        n_rep, warm, n = 2 * cores, 20000, args.cpu_steps
+        v, counters, wall = cpu_pool_run(blob, rates, n_rep, warm, n, cores)
+        if world == 1:
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d replicas spread over the grid x %d steps (after %d warm-up), %.1f s wall"
+                             % (n_rep, n, warm, wall)}
+
+    import torch
+    from kmos_b200 import engine
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.Stream()
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    seeds = (np.arange(REPLICAS_PER_GPU, dtype=np.uint64) + np.uint64(rank * REPLICAS_PER_GPU)) * np.uint64(2654435761) + np.uint64(17)
+    ids = (np.arange(REPLICAS_PER_GPU) + rank * REPLICAS_PER_GPU).astype(np.uint32)
+    batch = engine.Batch(model, REPLICAS_PER_GPU, SIZE, device=local_rank, seeds=seeds, replica_ids=ids, rates=rates)
+    batch.set_stream(stream.cuda_stream)
+    kinfo = batch.kernel_info()
+    assert kinfo["kernel_name"] == "smem", kinfo
+    n_groups = N_T * N_P
+    words = batch.tally_words()
+    tally = torch.zeros(n_groups * words, dtype=torch.float64, device="cuda")
+    smem_peak, _mhz = engine.measure_smem_bandwidth(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(kernel_events=None):
+        with torch.cuda.stream(stream):
+            if kernel_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            batch.do_steps(args.inner)
+            if kernel_events is not None:
+                e1.record(stream)
+                kernel_events.append((e0, e1))
+            batch.reduce_tallies(group_of, n_groups, dev_ptr=tally.data_ptr(), want_host=False)
+            if world > 1:
+                dist.all_reduce(tally)
+
+    # ---- device-resident throughput ("value") -----------------------------------------------------------
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kev = []
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record(stream)
+    for _ in range(args.steps):
+        one_step(kev)
+    t1.record(stream)
+    barrier()
+    ms = t0.elapsed_time(t1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, kernel_ms = t.tolist()
+    status_ok = bool(np.all(batch.status == 0))
+    steps_done = int(batch.kmc_step.min())
+
+    # ---- end to end through the public API with host buffers ("e2e") -------------------------------------
+    pinned = torch.from_numpy(np.ascontiguousarray(rates)).pin_memory()
+    rates_pinned = pinned.numpy()
+    host_tally = np.zeros((n_groups, words))
+
+    def one_step_e2e():
+        batch.set_rates(rates_pinned)                       # H2D of this step's inputs (pinned host memory)
+        batch.do_steps(args.inner)
+        t = batch.reduce_tallies(group_of, n_groups, dev_ptr=tally.data_ptr(), want_host=(world == 1))
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(tally)
+                t = tally.cpu().numpy().reshape(n_groups, words)  # D2H of the step's result
+            stream.synchronize()
+        host_tally[:] = t
+
+    for _ in range(max(1, args.warmup // 2)):
+        one_step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    total_steps = float(REPLICAS_PER_GPU) * args.inner * args.steps * world
+    if rank == 0:
+        value = total_steps / (ms * 1e-3)
+        b_step = algorithmic_bytes_per_step(P, counters)
+        launch_bytes = b_step * REPLICAS_PER_GPU * args.inner
+        achieved = launch_bytes / (kernel_ms * 1e-3) / 1e9
+        peaks = {}
+        try:
+            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except (OSError, ValueError):
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        ncu = {}
+        try:
+            with open(os.path.join(REPO, "profiles", "ncu_summary_r1.json")) as f:
+                ncu = json.load(f)
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(grid, args, extra={
+                "l2": "state per step (%d MB/GPU) exceeds the 126 MB L2; state is shared-memory resident during "
+                      "a launch" % (REPLICAS_PER_GPU * kinfo["state_bytes_per_replica"] // 2**20),
+                "kernel": kinfo, "all_replicas_ok": status_ok, "kmc_steps_per_replica_total": steps_done}),
+            "clocks": clocks,
+            "e2e": {"value": total_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(rates.nbytes), "d2h_bytes_per_step": int(host_tally.nbytes),
+                    "timing": "host wall clock, synchronized both sides, max over ranks"},
+            "gpu_launches": 3 * args.steps,
+            "roofline": {
+                "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
+                "frac": achieved / smem_peak if smem_peak else None,
+                "traffic": ncu.get("dram_bytes_per_launch"),
+                "kernel": "kb_smem_kernel", "kernel_ms_per_launch": kernel_ms,
+                "kernel_share_of_step": kernel_ms * args.steps / ms,
+                "algorithmic_bytes_per_kmc_step": b_step, "event_counters_per_step": counters,
+                "peak_source": "live LDS.128 streaming microbenchmark on this GPU (kmos_b200_measure_smem_bandwidth)",
+                "hbm": {"achieved": achieved, "peak": hbm_peak, "frac": achieved / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+                "note": "latency-bound by construction: one replica is a serial dependency chain (DESIGN.md)",
+            },
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--inner", type=int, default=5000, help="kMC steps per replica per bench step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=400000, help="kMC steps per replica of the CPU sample")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

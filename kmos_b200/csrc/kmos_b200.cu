@@ -62,6 +62,7 @@ struct kmos_b200_batch {
     uint16_t* image;     // compact avail planes of the shared-memory engine [R][img_bytes/2]
     bool compact_valid;  // true: `image` holds the avail tables, p1/p2 are stale; false: the other way round
     double* tally;
+    double* occ;  // scratch of reduce_tallies: occupation[R][n_species*spuck]
     int32_t* group_of;
     int tally_groups;
     // kernel choice
@@ -362,7 +363,7 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     memset(sc.data(), 0, sc.size() * sizeof(KbScalars));
     for (int r = 0; r < R; ++r) { sc[r].seed = 1; sc[r].replica = (uint32_t)r; }
     CU(cudaMemcpy(b->sc, sc.data(), sc.size() * sizeof(KbScalars), cudaMemcpyHostToDevice));
-    b->tally = nullptr; b->group_of = nullptr; b->tally_groups = 0;
+    b->tally = nullptr; b->occ = nullptr; b->group_of = nullptr; b->tally_groups = 0;
     plan_smem(b);
     b->image = nullptr;
     b->compact_valid = false;
@@ -378,7 +379,7 @@ extern "C" void kmos_b200_batch_destroy(kmos_b200_batch* b) {
     cudaStreamSynchronize(b->stream);
     cudaFree(b->d_blob); cudaFree(b->lattice); cudaFree(b->p1); cudaFree(b->p2); cudaFree(b->nsites);
     cudaFree(b->rates); cudaFree(b->integ); cudaFree(b->accum); cudaFree(b->procstat); cudaFree(b->sc);
-    cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->group_of); cudaFree(b->image);
+    cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->occ); cudaFree(b->group_of); cudaFree(b->image);
     cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
     cudaStreamDestroy(b->own_stream);
     delete b;
@@ -717,8 +718,8 @@ extern "C" int kmos_b200_reduce_tallies(kmos_b200_batch* b, const int32_t* group
         if (!b->group_of) CU(cudaMalloc(&b->group_of, (size_t)b->R * 4));
         CU(cudaMemcpyAsync(b->group_of, group_of, (size_t)b->R * 4, cudaMemcpyHostToDevice, b->stream));
     }
-    double* occ = nullptr;
-    CU(cudaMalloc(&occ, (size_t)b->R * nocc * 8));
+    if (!b->occ) CU(cudaMalloc(&b->occ, (size_t)b->R * nocc * 8));
+    double* occ = b->occ;
     double* out = (double*)dev_out;
     if (!out) {
         if (b->tally_groups < n_groups) {
@@ -729,14 +730,15 @@ extern "C" int kmos_b200_reduce_tallies(kmos_b200_batch* b, const int32_t* group
         out = b->tally;
     }
     int rc = compute_occupation(b, occ);
-    if (rc) { cudaFree(occ); return rc; }
+    if (rc) return rc;
     CU(cudaMemsetAsync(out, 0, (size_t)n_groups * words * 8, b->stream));
     kb_tally_kernel<<<(words + 63) / 64, 64, 0, b->stream>>>(b->sc, b->procstat, b->integ, occ,
                                                             group_of ? b->group_of : nullptr, b->R, m.n_proc, nocc, out, words);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(b->stream));
-    cudaFree(occ);
-    if (host_out) CU(cudaMemcpy(host_out, out, (size_t)n_groups * words * 8, cudaMemcpyDeviceToHost));
+    if (host_out) {  // asynchronous for callers that consume the device buffer (NCCL) themselves
+        CU(cudaStreamSynchronize(b->stream));
+        CU(cudaMemcpy(host_out, out, (size_t)n_groups * words * 8, cudaMemcpyDeviceToHost));
+    }
     return KMOS_B200_OK;
 }
 

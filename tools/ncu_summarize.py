@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Summarise ncu artefacts into profiles/ (tracked): per-kernel launch shares from a launch list CSV and the
+headline counters of a `--set full` capture of the step kernel."""
+import csv
+import json
+import subprocess
+import sys
+from collections import defaultdict
+
+
+def launch_list(path):
+    """ncu --metrics gpu__time_duration.sum --csv log -> {kernel: (launches, total_us)}"""
+    rows = []
+    with open(path) as f:
+        lines = [ln for ln in f if ln.startswith('"')]
+    rd = csv.DictReader(lines)
+    agg = defaultdict(lambda: [0, 0.0])
+    for r in rd:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = r["Kernel Name"].split("(")[0]
+        val = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        us = val / 1e3 if unit == "ns" else (val if unit == "us" else val * 1e3 if unit == "ms" else val)
+        agg[name][0] += 1
+        agg[name][1] += us
+    total = sum(v[1] for v in agg.values()) or 1.0
+    return {k: {"launches": v[0], "total_us": v[1], "share": v[1] / total} for k, v in
+            sorted(agg.items(), key=lambda kv: -kv[1][1])}
+
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_active.avg",
+        "sm__inst_executed.avg.per_cycle_active", "sm__warps_active.avg.per_cycle_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "smsp__average_warp_latency_per_inst_issued.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
+
+
+def full_capture(rep):
+    out = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], stderr=subprocess.DEVNULL).decode()
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {}
+    for h, u, v in zip(hdr, units, vals):
+        if h in KEYS or h == "Kernel Name":
+            d[h] = {"value": v, "unit": u}
+    return d
+
+
+if __name__ == "__main__":
+    mode, src, dst = sys.argv[1], sys.argv[2], sys.argv[3]
+    res = launch_list(src) if mode == "launches" else full_capture(src)
+    with open(dst, "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+    print(json.dumps(res, indent=1)[:3000])
