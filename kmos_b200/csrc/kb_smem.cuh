@@ -288,7 +288,11 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
     cc.magic_x = prm.magic_x; cc.magic_xy = prm.magic_xy;
     const uint32_t k0 = (uint32_t)sc.seed, k1 = (uint32_t)(sc.seed >> 32);
     const uint32_t my_off = lane < n_off ? offsets[lane] : 0u;
-    const int P32 = (min(P, 32) + 3) & ~3;  // entries of the first chain pass (prodS is zero padded)
+    const int n1 = min(P, 32), n2 = max(P - 32, 0);
+    double* Z1 = prodS;       // [n1 zeros][x_0 .. x_{n1-1}] (64 doubles reserved)
+    double* Z2 = prodS + 64;  // [n2 zeros][x_32 ..]         (64 doubles reserved)
+    for (int i = lane; i < 128; i += 32) prodS[i] = 0.0;
+    __syncwarp();
     const int lastp = P - 1;
 
     double rng_a = 0.0, rng_b = 0.0;  // even lanes: (-log(ran_time), ran_proc); odd lanes: (ran_site, -)
@@ -314,29 +318,24 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         const int n1 = has1 ? nS[q1] : 0;
         const double pr0 = __dmul_rn((double)n0, rate0);
         const double pr1 = __dmul_rn((double)n1, rate1);
-        prodS[q0] = pr0;
-        if (PPL == 2) prodS[q1] = pr1;
+        // Lane L must end up with accum_rates(L+1) = ((x_0 + x_1) + ...) + x_L.  The products sit behind n1
+        // leading zeros; lane L starts L+1 entries in, so after n1 additions it has added zeros (exact)
+        // followed by x_0..x_L in order -- no per-lane masking, one LDS + one DADD per process.
+        if (has0) Z1[n1 + q0] = pr0;
+        if (has1) Z2[n2 + lane] = pr1;
         __syncwarp();
         double acc0 = 0.0;
         {
-            const double2* pp = reinterpret_cast<const double2*>(prodS);
-            for (int j = 0; j < P32; j += 4) {
-                const double2 a = pp[j >> 1], b = pp[(j >> 1) + 1];
-                if (j <= lane) acc0 = __dadd_rn(acc0, a.x);
-                if (j + 1 <= lane) acc0 = __dadd_rn(acc0, a.y);
-                if (j + 2 <= lane) acc0 = __dadd_rn(acc0, b.x);
-                if (j + 3 <= lane) acc0 = __dadd_rn(acc0, b.y);
-            }
+            const double* src = Z1 + lane + 1;
+#pragma unroll 4
+            for (int t = 0; t < n1; ++t) acc0 = __dadd_rn(acc0, src[t]);
         }
         double acc1 = 0.0;
         if (PPL == 2) {
-            acc1 = __shfl_sync(KB_FULL, acc0, 31);
-            const double2* pp = reinterpret_cast<const double2*>(prodS);
-            for (int j = 32; j < P; j += 2) {
-                const double2 a = pp[j >> 1];
-                if (j <= q1) acc1 = __dadd_rn(acc1, a.x);
-                if (j + 1 <= q1) acc1 = __dadd_rn(acc1, a.y);
-            }
+            acc1 = __shfl_sync(KB_FULL, acc0, 31);  // accum_rates(32)
+            const double* src = Z2 + lane + 1;
+#pragma unroll 4
+            for (int t = 0; t < n2; ++t) acc1 = __dadd_rn(acc1, src[t]);
         }
         const double total = __shfl_sync(KB_FULL, (PPL == 2 && lastp >= 32) ? acc1 : acc0, lastp & 31);
         if (!(total > 0.0)) { status = KB_DEADLOCK; break; }

@@ -199,20 +199,24 @@ __global__ void kb_occupation_kernel(const uint8_t* lattice, int lat_stride, int
 }
 
 // tallies per group: [P] procstat | [P] integ | [ns*spuck] occupation | kmc_time | kmc_steps | n_replicas
+// One block per group; thread w owns word w and adds the group's replicas in replica order (deterministic).
 __global__ void kb_tally_kernel(const KbScalars* sc, const int64_t* procstat, const double* integ, const double* occ,
                                 const int32_t* group_of, int R, int P, int nocc, double* out, int words) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= words) return;
-    for (int rep = 0; rep < R; ++rep) {
-        double v;
-        if (w < P) v = (double)procstat[(size_t)rep * P + w];
-        else if (w < 2 * P) v = integ[(size_t)rep * P + (w - P)];
-        else if (w < 2 * P + nocc) v = occ[(size_t)rep * nocc + (w - 2 * P)];
-        else if (w == 2 * P + nocc) v = sc[rep].kmc_time;
-        else if (w == 2 * P + nocc + 1) v = (double)sc[rep].kmc_step;
-        else v = 1.0;
-        int grp = group_of ? group_of[rep] : 0;
-        out[(size_t)grp * words + w] += v;  // one thread owns word w of every group: no race
+    const int grp = blockIdx.x;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        double acc = 0.0;
+        for (int rep = 0; rep < R; ++rep) {
+            if ((group_of ? group_of[rep] : 0) != grp) continue;
+            double v;
+            if (w < P) v = (double)procstat[(size_t)rep * P + w];
+            else if (w < 2 * P) v = integ[(size_t)rep * P + (w - P)];
+            else if (w < 2 * P + nocc) v = occ[(size_t)rep * nocc + (w - 2 * P)];
+            else if (w == 2 * P + nocc) v = sc[rep].kmc_time;
+            else if (w == 2 * P + nocc + 1) v = (double)sc[rep].kmc_step;
+            else v = 1.0;
+            acc += v;
+        }
+        out[(size_t)grp * words + w] = acc;
     }
 }
 
@@ -258,8 +262,8 @@ static void plan_smem(kmos_b200_batch* b) {
     sp.dev_words = m->h.dev_len;
     sp.tab_bytes = (int)align_up((size_t)sp.dev_words * 4, 128);
     sp.n_classes = d[10]; sp.n_arenas = d[11];
-    sp.cap = (b->g.ncells + d[13] + 1) & ~1;  // spare slots: lists of an arena may overlap transiently by
-                                              // at most the number of adds of one event
+    sp.cap = (b->g.ncells + d[15] + 1) & ~1;  // spare slots: the two lists of an arena may overshoot ncells
+                                              // transiently by at most the adds of one event (devtables.py)
     sp.plane_bytes = (int)b->plane_bytes;
     sp.lat_stride = b->lat_stride;
     const size_t img = ((size_t)sp.n_arenas * sp.cap + (size_t)sp.n_classes * b->g.ncells) * 2;
@@ -268,7 +272,7 @@ static void plan_smem(kmos_b200_batch* b) {
     sp.off_lat = sp.img_bytes;
     sp.off_ns = sp.off_lat + sp.lat_stride;
     sp.off_prod = (int)align_up((size_t)sp.off_ns + 4 * m->h.n_proc, 16);
-    sp.off_mbar = sp.off_prod + 8 * (m->h.n_proc > 32 ? 64 : 32);
+    sp.off_mbar = sp.off_prod + 8 * 128;  // two zero-prefixed product buffers (kb_smem.cuh)
     sp.rep_bytes = (int)align_up((size_t)sp.off_mbar + 16, 128);
     int best_w = 0, best_c = 0, best_total = 0;
     for (int w = 1; w <= 16; ++w) {
@@ -731,8 +735,7 @@ extern "C" int kmos_b200_reduce_tallies(kmos_b200_batch* b, const int32_t* group
     }
     int rc = compute_occupation(b, occ);
     if (rc) return rc;
-    CU(cudaMemsetAsync(out, 0, (size_t)n_groups * words * 8, b->stream));
-    kb_tally_kernel<<<(words + 63) / 64, 64, 0, b->stream>>>(b->sc, b->procstat, b->integ, occ,
+    kb_tally_kernel<<<n_groups, 128, 0, b->stream>>>(b->sc, b->procstat, b->integ, occ,
                                                             group_of ? b->group_of : nullptr, b->R, m.n_proc, nocc, out, words);
     CU(cudaGetLastError());
     if (host_out) {  // asynchronous for callers that consume the device buffer (NCCL) themselves

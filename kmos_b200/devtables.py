@@ -33,7 +33,7 @@ disjoint memory and run one per lane.
 Section layout (int32 words, offsets relative to the section start):
     [0] version=2 [1] supported [2] n_events [3] events_off [4] ops_off [5] n_ops [6] op_stride
     [7] offsets_off [8] n_offsets [9] procinfo_off [10] n_classes [11] n_arenas [12] max_rounds
-    [13] max_ops_per_event [14] max_ncond [15] reserved
+    [13] max_ops_per_event [14] max_ncond [15] spare slots per arena (most adds of one event into one arena)
     events   EVENT_WORDS each: w0 = ops_start | n_rounds<<16 | n_writes<<20 | min_q<<24
                                w1,w2 = cumulative op count after each round (8 x u8), w3 = 0
                                w4..w7 = writes: off_id | n<<5 | old<<8 | new<<12
@@ -255,15 +255,30 @@ def compile_device_tables(ir, asm=None):
         classes, cls_of, member_of = exclusivity_classes(ir, proc_anchor)
         if len(classes) > 32:
             raise Unsupported("more than 32 exclusivity classes")
-        # arenas: consecutive members of a class share one (left list, right list)
+        # arenas: two mutually exclusive processes share one (left list, right list); pairs are chosen by
+        # a greedy maximum matching on the exclusivity graph (not restricted to one class)
+        conds = process_conditions(ir)
+        partner = {}
+        order = sorted(range(1, nproc + 1), key=lambda q: sum(
+            1 for c in range(1, nproc + 1) if c != q and q in conds and c in conds
+            and proc_anchor[c - 1] == proc_anchor[q - 1] and exclusive(conds[q], conds[c])))
+        for q in order:
+            if q in partner or q not in conds:
+                continue
+            for c in order:
+                if c != q and c not in partner and c in conds and proc_anchor[c - 1] == proc_anchor[q - 1] \
+                        and exclusive(conds[q], conds[c]):
+                    partner[q], partner[c] = c, q
+                    break
         arena_of, dir_of = {}, {}
         n_arenas = 0
-        for cl in classes:
-            for i in range(0, len(cl), 2):
-                arena_of[cl[i]], dir_of[cl[i]] = n_arenas, 0
-                if i + 1 < len(cl):
-                    arena_of[cl[i + 1]], dir_of[cl[i + 1]] = n_arenas, 1
-                n_arenas += 1
+        for q in range(1, nproc + 1):
+            if q in arena_of:
+                continue
+            arena_of[q], dir_of[q] = n_arenas, 0
+            if q in partner:
+                arena_of[partner[q]], dir_of[partner[q]] = n_arenas, 1
+            n_arenas += 1
         if n_arenas > 64:
             raise Unsupported("more than 64 arenas")
 
@@ -301,6 +316,13 @@ def compile_device_tables(ir, asm=None):
 
         ops_words, events_words, stats = [], [], []
         max_rounds = max_ops = 0
+        spare = 0
+        for _b, _w, ops in flat:
+            per_arena = {}
+            for kind, q, _a, _c, _g in ops:
+                if kind == KIND_ADD:
+                    per_arena[arena_of[q]] = per_arena.get(arena_of[q], 0) + 1
+            spare = max([spare] + list(per_arena.values()))
         for p, (base_n, writes, ops) in enumerate(flat):
             rounds = schedule_rounds(ops, lambda op: [op[1]],
                                      lambda op: (cls_of[op[1]], op[2][0], op[2][1], op[2][2]))
@@ -354,10 +376,10 @@ def compile_device_tables(ir, asm=None):
     offsets_off = ops_off + len(ops_words)
     procinfo_off = offsets_off + len(offsets_words)
     header = [DEV_VERSION, 1, nproc, events_off, ops_off, len(ops_words) // op_stride, op_stride, offsets_off,
-              len(offsets_words), procinfo_off, len(classes), n_arenas, max_rounds, max_ops, max_ncond, 0]
+              len(offsets_words), procinfo_off, len(classes), n_arenas, max_rounds, max_ops, max_ncond, spare]
     words = header + events_words + ops_words + offsets_words + procinfo
     info.update({"supported": True, "n_ops": len(ops_words) // op_stride, "op_stride": op_stride,
                  "n_offsets": len(offsets_words), "n_classes": len(classes), "n_arenas": n_arenas,
-                 "classes": classes, "max_rounds": max_rounds, "max_ops": max_ops, "max_ncond": max_ncond,
+                 "classes": classes, "spare": spare, "max_rounds": max_rounds, "max_ops": max_ops, "max_ncond": max_ncond,
                  "per_event": stats, "bytes": 4 * len(words), "proc_anchor": proc_anchor})
     return [s32(w) for w in words], info

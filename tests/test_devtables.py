@@ -39,7 +39,7 @@ class EventModel(object):
         self.spuck = o.spuck
         self.P = o.n_proc
         self.C = o.volume // o.spuck
-        self.cap = self.C + (d[13] if spare is None else spare)
+        self.cap = self.C + (d[15] if spare is None else spare)
         self.rng = np.random.RandomState(5)
         self.lattice = o.lattice.copy()
         self.n = [int(x) for x in o.nr_of_sites]
