@@ -288,9 +288,9 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
     cc.magic_x = prm.magic_x; cc.magic_xy = prm.magic_xy;
     const uint32_t k0 = (uint32_t)sc.seed, k1 = (uint32_t)(sc.seed >> 32);
     const uint32_t my_off = lane < n_off ? offsets[lane] : 0u;
-    const int n1 = min(P, 32), n2 = max(P - 32, 0);
-    double* Z1 = prodS;       // [n1 zeros][x_0 .. x_{n1-1}] (64 doubles reserved)
-    double* Z2 = prodS + 64;  // [n2 zeros][x_32 ..]         (64 doubles reserved)
+    const int len1 = min(P, 32), len2 = max(P - 32, 0);
+    double* Z1 = prodS;       // [len1 zeros][x_0 .. x_{len1-1}] (64 doubles reserved)
+    double* Z2 = prodS + 64;  // [len2 zeros][x_32 ..]           (64 doubles reserved)
     for (int i = lane; i < 128; i += 32) prodS[i] = 0.0;
     __syncwarp();
     const int lastp = P - 1;
@@ -318,24 +318,24 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         const int n1 = has1 ? nS[q1] : 0;
         const double pr0 = __dmul_rn((double)n0, rate0);
         const double pr1 = __dmul_rn((double)n1, rate1);
-        // Lane L must end up with accum_rates(L+1) = ((x_0 + x_1) + ...) + x_L.  The products sit behind n1
-        // leading zeros; lane L starts L+1 entries in, so after n1 additions it has added zeros (exact)
+        // Lane L must end up with accum_rates(L+1) = ((x_0 + x_1) + ...) + x_L.  The products sit behind len1
+        // leading zeros; lane L starts L+1 entries in, so after len1 additions it has added zeros (exact)
         // followed by x_0..x_L in order -- no per-lane masking, one LDS + one DADD per process.
-        if (has0) Z1[n1 + q0] = pr0;
-        if (has1) Z2[n2 + lane] = pr1;
+        if (has0) Z1[len1 + q0] = pr0;
+        if (has1) Z2[len2 + lane] = pr1;
         __syncwarp();
         double acc0 = 0.0;
         {
             const double* src = Z1 + lane + 1;
 #pragma unroll 4
-            for (int t = 0; t < n1; ++t) acc0 = __dadd_rn(acc0, src[t]);
+            for (int t = 0; t < len1; ++t) acc0 = __dadd_rn(acc0, src[t]);
         }
         double acc1 = 0.0;
         if (PPL == 2) {
             acc1 = __shfl_sync(KB_FULL, acc0, 31);  // accum_rates(32)
             const double* src = Z2 + lane + 1;
 #pragma unroll 4
-            for (int t = 0; t < n2; ++t) acc1 = __dadd_rn(acc1, src[t]);
+            for (int t = 0; t < len2; ++t) acc1 = __dadd_rn(acc1, src[t]);
         }
         const double total = __shfl_sync(KB_FULL, (PPL == 2 && lastp >= 32) ? acc1 : acc0, lastp & 31);
         if (!(total > 0.0)) { status = KB_DEADLOCK; break; }
