@@ -59,7 +59,8 @@ struct KbSmemParams {
     int R;
     long long nsteps;
     // shared-memory layout (bytes)
-    int tab_bytes, rep_bytes, off_p2, off_lat, off_ns, off_prod, off_mbar;
+    int tab_bytes, rep_bytes, off_hi, off_p2, off_lat, off_ns, off_prod, off_mbar;
+    int split;        // 1: plane 1 stored as low bytes + a bitmap of bit 8 (ncells <= 512), 0: uint16
     int lat_stride;   // bytes, multiple of 16
     int img_bytes;    // bytes of the compact image (both planes), multiple of 16
     int plane_bytes;  // bytes of one canonical plane, multiple of 16
@@ -116,6 +117,31 @@ __device__ __forceinline__ int kb_slot(int arena, int dir, int cap, int k) {
     return arena * cap + (dir ? cap - 1 - k : k);
 }
 
+// Plane-1 accessors.  SPLIT: a cell index < 512 is stored as its low byte plus one bit in a bitmap
+// (1.125 B per slot instead of 2): for 20x20 lattices this is what lets 13 instead of 9 replicas share an SM.
+// Slots of one byte of the bitmap belong to one list (the two lists of an arena stay >= 8 slots apart, see
+// the spare-slot rule in plan_smem), and ops on one list are serialised by the round schedule.
+template <bool SPLIT>
+__device__ __forceinline__ int kb_p1_get(const unsigned char* p1, const unsigned char* hi, int slot) {
+    if (SPLIT) {
+        const uint32_t lo = p1[slot];
+        const uint32_t hb = hi[slot >> 3];
+        return (int)(lo | (((hb >> (slot & 7)) & 1u) << 8));
+    }
+    return (int)reinterpret_cast<const uint16_t*>(p1)[slot];
+}
+template <bool SPLIT>
+__device__ __forceinline__ void kb_p1_set(unsigned char* p1, unsigned char* hi, int slot, int cell) {
+    if (SPLIT) {
+        p1[slot] = (unsigned char)cell;
+        const uint32_t bit = 1u << (slot & 7);
+        const uint32_t hb = hi[slot >> 3];
+        hi[slot >> 3] = (unsigned char)((cell & 256) ? (hb | bit) : (hb & ~bit));
+    } else {
+        reinterpret_cast<uint16_t*>(p1)[slot] = (uint16_t)cell;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // canonical <-> compact conversion (one warp per replica, runs between engine switches only)
 // ---------------------------------------------------------------------------------------------------
@@ -125,11 +151,11 @@ __global__ void kb_pack_kernel(const KbSmemParams prm) {
     if (rep >= prm.R) return;
     const int P = prm.n_proc, C = prm.ncells, cap = prm.cap;
     const int32_t* procinfo = prm.dev + prm.dev[9];
-    uint16_t* img = prm.image + (size_t)rep * (prm.img_bytes / 2);
-    uint16_t* cp2 = img + (size_t)prm.n_arenas * cap;
+    unsigned char* img = reinterpret_cast<unsigned char*>(prm.image) + (size_t)rep * prm.img_bytes;
+    uint16_t* cp2 = reinterpret_cast<uint16_t*>(img + prm.off_p2);
     const uint16_t* g1 = prm.p1 + (size_t)rep * (prm.plane_bytes / 2);
     const int32_t* ns = prm.nsites + (size_t)rep * P;
-    for (int i = lane; i < prm.img_bytes / 2; i += 32) img[i] = 0;
+    for (int i = lane; i < prm.img_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(img)[i] = 0;
     __syncwarp();
     for (int q = 0; q < P; ++q) {
         const uint32_t pi = (uint32_t)procinfo[q];
@@ -137,8 +163,26 @@ __global__ void kb_pack_kernel(const KbSmemParams prm) {
         const int n = ns[q];
         for (int k = lane; k < n; k += 32) {
             const int cell = g1[(size_t)q * C + k];
-            img[kb_slot(arena, dir, cap, k)] = (uint16_t)cell;
+            if (!prm.split) reinterpret_cast<uint16_t*>(img)[kb_slot(arena, dir, cap, k)] = (uint16_t)cell;
+            else img[kb_slot(arena, dir, cap, k)] = (unsigned char)cell;
             cp2[(size_t)cls * C + cell] = (uint16_t)((member << KB_POS_BITS) | (k + 1));
+        }
+        if (prm.split) {  // bit 8 of every slot, one bitmap byte per lane and pass (no shared bytes)
+            __syncwarp();
+            unsigned char* hi = img + prm.off_hi;
+            const int first = dir ? cap - n : 0;  // slots [first, first+n) of this arena
+            for (int b = (first >> 3) + lane; b <= ((first + n - 1) >> 3) && n > 0; b += 32) {
+                uint32_t byte = hi[(arena * cap >> 3) + b];
+                for (int j = 0; j < 8; ++j) {
+                    const int sl = b * 8 + j;
+                    if (sl < first || sl >= first + n) continue;
+                    const int k = dir ? cap - 1 - sl : sl;
+                    const int cell = g1[(size_t)q * C + k];
+                    byte = (cell & 256) ? (byte | (1u << j)) : (byte & ~(1u << j));
+                }
+                hi[(arena * cap >> 3) + b] = (unsigned char)byte;
+            }
+            __syncwarp();
         }
     }
 }
@@ -149,7 +193,7 @@ __global__ void kb_unpack_kernel(const KbSmemParams prm) {
     if (rep >= prm.R) return;
     const int P = prm.n_proc, C = prm.ncells, cap = prm.cap;
     const int32_t* procinfo = prm.dev + prm.dev[9];
-    const uint16_t* img = prm.image + (size_t)rep * (prm.img_bytes / 2);
+    const unsigned char* img = reinterpret_cast<const unsigned char*>(prm.image) + (size_t)rep * prm.img_bytes;
     uint16_t* g1 = prm.p1 + (size_t)rep * (prm.plane_bytes / 2);
     uint16_t* g2 = prm.p2 + (size_t)rep * (prm.plane_bytes / 2);
     const int32_t* ns = prm.nsites + (size_t)rep * P;
@@ -160,7 +204,8 @@ __global__ void kb_unpack_kernel(const KbSmemParams prm) {
         const int arena = pi & 63, dir = (pi >> 6) & 1;
         const int n = ns[q];
         for (int k = lane; k < n; k += 32) {
-            const int cell = img[kb_slot(arena, dir, cap, k)];
+            const int sl = kb_slot(arena, dir, cap, k);
+            const int cell = prm.split ? kb_p1_get<true>(img, img + prm.off_hi, sl) : kb_p1_get<false>(img, img, sl);
             g1[(size_t)q * C + k] = (uint16_t)cell;
             g2[(size_t)q * C + cell] = (uint16_t)(k + 1);
         }
@@ -212,7 +257,7 @@ struct KbCellCtx {
 };
 
 // PPL: processes per lane (1: P <= 32, 2: P <= 64);  NCOND: largest number of dynamic probes of an add
-template <int PPL, int NCOND>
+template <int PPL, int NCOND, bool SPLIT>
 __global__ void kb_smem_kernel(const KbSmemParams prm) {
     extern __shared__ __align__(128) unsigned char kb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -231,7 +276,8 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
     constexpr int STRIDE = 1 + NCOND;
 
     unsigned char* base = kb_smem + prm.tab_bytes + (size_t)warp * prm.rep_bytes;
-    uint16_t* p1 = reinterpret_cast<uint16_t*>(base);
+    unsigned char* p1 = base;
+    unsigned char* p1hi = base + prm.off_hi;
     uint16_t* p2 = reinterpret_cast<uint16_t*>(base + prm.off_p2);
     uint8_t* lat = base + prm.off_lat;
     int32_t* nS = reinterpret_cast<int32_t*>(base + prm.off_ns);
@@ -239,7 +285,7 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
     uint64_t* mbar = reinterpret_cast<uint64_t*>(base + prm.off_mbar);
 
     const int P = prm.n_proc, C = prm.ncells, cap = prm.cap, spuck = prm.spuck;
-    uint16_t* g_img = prm.image + (size_t)rep * (prm.img_bytes / 2);
+    unsigned char* g_img = reinterpret_cast<unsigned char*>(prm.image) + (size_t)rep * prm.img_bytes;
     uint8_t* g_lat = prm.lattice + (size_t)rep * prm.lat_stride;
     int32_t* g_ns = prm.nsites + (size_t)rep * P;
 
@@ -364,7 +410,7 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         int k = (int)__dadd_rn(1.0, __dmul_rn(ran_site, (double)nsel));
         k = min(k, nsel);
         const uint32_t spi = procinfo[pidx];
-        const int cell = (int)p1[kb_slot((int)(spi & 63u), (int)((spi >> 6) & 1u), cap, k - 1)];
+        const int cell = kb_p1_get<SPLIT>(p1, p1hi, kb_slot((int)(spi & 63u), (int)((spi >> 6) & 1u), cap, k - 1));
         if ((pidx & 31) == lane) {
             if (PPL == 2 && pidx >= 32) ps1 += 1; else ps0 += 1;
         }
@@ -417,7 +463,7 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
                     if (nq >= C || entry[ca] != 0) {
                         status = KB_CAPACITY;
                     } else {
-                        p1[kb_slot(arena, dir, cap, nq)] = (uint16_t)ca;
+                        kb_p1_set<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, nq), ca);
                         entry[ca] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)(nq + 1));
                         nS[q] = nq + 1;
                     }
@@ -426,9 +472,9 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
                     if ((e >> KB_POS_BITS) == member) {
                         const int pos = (int)(e & KB_POS_MASK);
                         const int nq = nS[q];
-                        const uint16_t last = p1[kb_slot(arena, dir, cap, nq - 1)];
+                        const int last = kb_p1_get<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, nq - 1));
                         if (pos < nq) {
-                            p1[kb_slot(arena, dir, cap, pos - 1)] = last;
+                            kb_p1_set<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, pos - 1), last);
                             entry[last] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)pos);
                         }
                         entry[ca] = 0;

@@ -262,13 +262,18 @@ static void plan_smem(kmos_b200_batch* b) {
     sp.dev_words = m->h.dev_len;
     sp.tab_bytes = (int)align_up((size_t)sp.dev_words * 4, 128);
     sp.n_classes = d[10]; sp.n_arenas = d[11];
-    sp.cap = (b->g.ncells + d[15] + 1) & ~1;  // spare slots: the two lists of an arena may overshoot ncells
-                                              // transiently by at most the adds of one event (devtables.py)
+    // spare slots: the two lists of an arena may overshoot ncells transiently by at most the adds of one
+    // event (devtables.py).  Split storage additionally keeps the lists >= 8 slots apart so that no byte of
+    // the bit-8 bitmap is shared between two lists.
+    const char* ns_env = getenv("KMOS_B200_NO_SPLIT");
+    sp.split = (b->g.ncells <= 512 && !(ns_env && ns_env[0] == '1')) ? 1 : 0;
+    sp.cap = sp.split ? (int)align_up((size_t)b->g.ncells + d[15] + 8, 8) : (b->g.ncells + d[15] + 1) & ~1;
     sp.plane_bytes = (int)b->plane_bytes;
     sp.lat_stride = b->lat_stride;
-    const size_t img = ((size_t)sp.n_arenas * sp.cap + (size_t)sp.n_classes * b->g.ncells) * 2;
-    sp.img_bytes = (int)align_up(img, 16);
-    sp.off_p2 = sp.n_arenas * sp.cap * 2;
+    const size_t p1_bytes = sp.split ? (size_t)sp.n_arenas * sp.cap : (size_t)sp.n_arenas * sp.cap * 2;
+    sp.off_hi = (int)p1_bytes;
+    sp.off_p2 = (int)align_up(p1_bytes + (sp.split ? (size_t)sp.n_arenas * sp.cap / 8 : 0), 4);
+    sp.img_bytes = (int)align_up((size_t)sp.off_p2 + (size_t)sp.n_classes * b->g.ncells * 2, 16);
     sp.off_lat = sp.img_bytes;
     sp.off_ns = sp.off_lat + sp.lat_stride;
     sp.off_prod = (int)align_up((size_t)sp.off_ns + 4 * m->h.n_proc, 16);
@@ -583,10 +588,14 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     sp.nsteps = n;
     const int threads = b->wpc * 32;
     const int blocks = (b->R + b->wpc - 1) / b->wpc;
-#define KB_LAUNCH(PPL, NC)                                                                                          \
-    do {                                                                                                            \
-        CU(cudaFuncSetAttribute(kb_smem_kernel<PPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes)); \
-        kb_smem_kernel<PPL, NC><<<blocks, threads, b->smem_bytes, b->stream>>>(sp);                                 \
+#define KB_LAUNCH_S(PPL, NC, SPL)                                                                                          \
+    do {                                                                                                                   \
+        CU(cudaFuncSetAttribute(kb_smem_kernel<PPL, NC, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes)); \
+        kb_smem_kernel<PPL, NC, SPL><<<blocks, threads, b->smem_bytes, b->stream>>>(sp);                                   \
+    } while (0)
+#define KB_LAUNCH(PPL, NC)                                             \
+    do {                                                               \
+        if (sp.split) KB_LAUNCH_S(PPL, NC, true); else KB_LAUNCH_S(PPL, NC, false); \
     } while (0)
 #define KB_LAUNCH_NC(PPL)                  \
     switch (b->ncond) {                    \
@@ -599,6 +608,7 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     if (b->ppl == 2) { KB_LAUNCH_NC(2) } else { KB_LAUNCH_NC(1) }
 #undef KB_LAUNCH_NC
 #undef KB_LAUNCH
+#undef KB_LAUNCH_S
     CU(cudaGetLastError());
     return KMOS_B200_OK;
 }

@@ -258,18 +258,39 @@ def compile_device_tables(ir, asm=None):
         # arenas: two mutually exclusive processes share one (left list, right list); pairs are chosen by
         # a greedy maximum matching on the exclusivity graph (not restricted to one class)
         conds = process_conditions(ir)
-        partner = {}
-        order = sorted(range(1, nproc + 1), key=lambda q: sum(
-            1 for c in range(1, nproc + 1) if c != q and q in conds and c in conds
-            and proc_anchor[c - 1] == proc_anchor[q - 1] and exclusive(conds[q], conds[c])))
-        for q in order:
-            if q in partner or q not in conds:
-                continue
-            for c in order:
-                if c != q and c not in partner and c in conds and proc_anchor[c - 1] == proc_anchor[q - 1] \
-                        and exclusive(conds[q], conds[c]):
-                    partner[q], partner[c] = c, q
-                    break
+
+        def can_pair(a, c):
+            return (a != c and a in conds and c in conds and proc_anchor[a - 1] == proc_anchor[c - 1]
+                    and exclusive(conds[a], conds[c]))
+
+        def greedy_matching(order):
+            match = {}
+            for q in order:
+                if q in match:
+                    continue
+                for c in order:
+                    if c not in match and can_pair(q, c):
+                        match[q], match[c] = c, q
+                        break
+            return match
+
+        candidates = []
+        # (a) neighbours inside each exclusivity class
+        m = {}
+        for cl in classes:
+            for i in range(0, len(cl) - 1, 2):
+                m[cl[i]], m[cl[i + 1]] = cl[i + 1], cl[i]
+        candidates.append(m)
+        # (b) greedy matchings: fewest possible partners first, then a few deterministic shuffles
+        degree = {q: sum(1 for c in range(1, nproc + 1) if can_pair(q, c)) for q in range(1, nproc + 1)}
+        candidates.append(greedy_matching(sorted(range(1, nproc + 1), key=lambda q: (degree[q], q))))
+        import random
+        rnd = random.Random(12345)
+        for _ in range(32):
+            order = list(range(1, nproc + 1))
+            rnd.shuffle(order)
+            candidates.append(greedy_matching(order))
+        partner = max(candidates, key=len)
         arena_of, dir_of = {}, {}
         n_arenas = 0
         for q in range(1, nproc + 1):
