@@ -52,7 +52,14 @@ class KMC_Model(object):
         self.site_names = list(self.ir["sites"])
         self.process_names = list(self.ir["procs"])
         # TOF bookkeeping (kmos/run/__init__.py:262-267)
-        tof_counts = {p["name"].lower(): p["tof_count"] for p in self.ir["process_defs"] if p.get("tof_count")}
+        tof_counts = {}
+        for p in self.ir["process_defs"]:
+            tc = p.get("tof_count")
+            if isinstance(tc, str):  # .ini models carry the dict as text: "{'TOF': 1}"
+                import ast
+                tc = ast.literal_eval(tc)
+            if tc:
+                tof_counts[p["name"].lower()] = tc
         self.tofs = sorted({name for tc in tof_counts.values() for name in tc})
         self.tof_matrix = np.zeros((len(self.tofs), self.model.n_proc))
         for i, pname in enumerate(self.process_names):
