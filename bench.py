@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
         return
     ir, blob, info, rates, group_of, grid = load_workload()
     cores = host_cores()
-    n_rep = 2 * cores
+    n_rep = 4 * cores
     warm, n = 20000, args.cpu_steps
     # untimed warm-up steps, then K timed steps; each step = the bounded sample below
     vals = []
@@ -206,7 +206,7 @@ def run_ours(args, rank, world, local_rank):
     counters = None
     if rank == 0:
         cores = host_cores()
-        n_rep, warm, n = 2 * cores, 20000, args.cpu_steps
+        n_rep, warm, n = 4 * cores, 20000, args.cpu_steps
         v, counters, wall = cpu_pool_run(blob, rates, n_rep, warm, n, cores)
         if world == 1:
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--inner", type=int, default=5000, help="kMC steps per replica per bench step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-steps", type=int, default=400000, help="kMC steps per replica of the CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=800000, help="kMC steps per replica of the CPU sample")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
