@@ -78,8 +78,10 @@ void kmos_b200_batch_destroy(kmos_b200_batch *b);
 int kmos_b200_batch_volume(const kmos_b200_batch *b); /* base.get_volume */
 int kmos_b200_select_kernel(kmos_b200_batch *b, int32_t kind);
 /* info[0]=kernel in use, [1]=replicas per CTA, [2]=dynamic smem bytes per CTA, [3]=CTAs per SM,
- * [4]=SM count, [5]=bytes of state per replica in shared memory, [6]=device table bytes, [7]=grid size */
-int kmos_b200_kernel_info(kmos_b200_batch *b, int64_t info[8]);
+ * [4]=SM count, [5]=bytes of state per replica in shared memory, [6]=device table bytes, [7]=grid size,
+ * [8]=1 if the avail-site lists stay in HBM/L2, [9]=registers per thread, [10]=1 if split list storage,
+ * [11]=bytes of the compact avail image per replica */
+int kmos_b200_kernel_info(kmos_b200_batch *b, int64_t info[12]);
 
 /* RNG: per-replica Philox4x32-10 stream, key = seed, counter = (kmc_step, replica_id, slot).
  * replaces: random_seed(put=seed_arr) in initialize_state (proclist_generic_subroutines.mpy:253-258).

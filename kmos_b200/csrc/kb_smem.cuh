@@ -59,8 +59,12 @@ struct KbSmemParams {
     int R;
     long long nsteps;
     // shared-memory layout (bytes)
-    int tab_bytes, rep_bytes, off_hi, off_p2, off_lat, off_ns, off_prod, off_mbar;
+    int tab_bytes, rep_bytes;
+    int off_hi, off_p2;                                   // offsets inside the compact image
+    int sm_p2, sm_lat, sm_ns, sm_prod, sm_mbar;           // offsets inside a replica's shared-memory block
+    int stage_off, stage_bytes;                           // part of the image that is staged into smem
     int split;        // 1: plane 1 stored as low bytes + a bitmap of bit 8 (ncells <= 512), 0: uint16
+    int p1_global;    // 1: plane 1 (the lists) stays in HBM/L2, only plane 2 + lattice live in shared memory
     int lat_stride;   // bytes, multiple of 16
     int img_bytes;    // bytes of the compact image (both planes), multiple of 16
     int plane_bytes;  // bytes of one canonical plane, multiple of 16
@@ -257,7 +261,7 @@ struct KbCellCtx {
 };
 
 // PPL: processes per lane (1: P <= 32, 2: P <= 64);  NCOND: largest number of dynamic probes of an add
-template <int PPL, int NCOND, bool SPLIT>
+template <int PPL, int NCOND, bool SPLIT, bool P1G>
 __global__ void kb_smem_kernel(const KbSmemParams prm) {
     extern __shared__ __align__(128) unsigned char kb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -276,16 +280,20 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
     constexpr int STRIDE = 1 + NCOND;
 
     unsigned char* base = kb_smem + prm.tab_bytes + (size_t)warp * prm.rep_bytes;
-    unsigned char* p1 = base;
-    unsigned char* p1hi = base + prm.off_hi;
-    uint16_t* p2 = reinterpret_cast<uint16_t*>(base + prm.off_p2);
-    uint8_t* lat = base + prm.off_lat;
-    int32_t* nS = reinterpret_cast<int32_t*>(base + prm.off_ns);
-    double* prodS = reinterpret_cast<double*>(base + prm.off_prod);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(base + prm.off_mbar);
+    uint16_t* p2 = reinterpret_cast<uint16_t*>(base + prm.sm_p2);
+    uint8_t* lat = base + prm.sm_lat;
+    int32_t* nS = reinterpret_cast<int32_t*>(base + prm.sm_ns);
+    double* prodS = reinterpret_cast<double*>(base + prm.sm_prod);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(base + prm.sm_mbar);
 
     const int P = prm.n_proc, C = prm.ncells, cap = prm.cap, spuck = prm.spuck;
     unsigned char* g_img = reinterpret_cast<unsigned char*>(prm.image) + (size_t)rep * prm.img_bytes;
+    // plane 1: in shared memory (staged with the rest of the image) or left in HBM/L2 (P1G): the lists are
+    // touched ~10x per step while plane 2 and the lattice take ~40 probes, so keeping only the latter in
+    // shared memory trades a few L2 round trips per step for 2-3x more resident replicas per SM
+    unsigned char* p1 = P1G ? g_img : base;
+    unsigned char* p1hi = p1 + prm.off_hi;
+    unsigned char* g_stage = g_img + prm.stage_off;
     uint8_t* g_lat = prm.lattice + (size_t)rep * prm.lat_stride;
     int32_t* g_ns = prm.nsites + (size_t)rep * P;
 
@@ -297,15 +305,15 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         }
         __syncwarp();
         if (lane == 0) {
-            kb_mbar_expect_tx(mbar, (uint32_t)(prm.img_bytes + prm.lat_stride));
-            kb_bulk_g2s(p1, g_img, (uint32_t)prm.img_bytes, mbar);
+            kb_mbar_expect_tx(mbar, (uint32_t)(prm.stage_bytes + prm.lat_stride));
+            kb_bulk_g2s(base, g_stage, (uint32_t)prm.stage_bytes, mbar);
             kb_bulk_g2s(lat, g_lat, (uint32_t)prm.lat_stride, mbar);
         }
         kb_mbar_wait(mbar, 0);
     } else {
-        const uint4* s1 = reinterpret_cast<const uint4*>(g_img);
-        uint4* d1 = reinterpret_cast<uint4*>(p1);
-        for (int i = lane; i < prm.img_bytes / 16; i += 32) d1[i] = s1[i];
+        const uint4* s1 = reinterpret_cast<const uint4*>(g_stage);
+        uint4* d1 = reinterpret_cast<uint4*>(base);
+        for (int i = lane; i < prm.stage_bytes / 16; i += 32) d1[i] = s1[i];
         const uint4* sl = reinterpret_cast<const uint4*>(g_lat);
         uint4* dl = reinterpret_cast<uint4*>(lat);
         for (int i = lane; i < prm.lat_stride / 16; i += 32) dl[i] = sl[i];
@@ -497,14 +505,14 @@ __global__ void kb_smem_kernel(const KbSmemParams prm) {
         kb_fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            kb_bulk_s2g(g_img, p1, (uint32_t)prm.img_bytes);
+            kb_bulk_s2g(g_stage, base, (uint32_t)prm.stage_bytes);
             kb_bulk_s2g(g_lat, lat, (uint32_t)prm.lat_stride);
             kb_bulk_commit_wait();
         }
     } else {
-        uint4* s1 = reinterpret_cast<uint4*>(g_img);
-        const uint4* d1 = reinterpret_cast<const uint4*>(p1);
-        for (int i = lane; i < prm.img_bytes / 16; i += 32) s1[i] = d1[i];
+        uint4* s1 = reinterpret_cast<uint4*>(g_stage);
+        const uint4* d1 = reinterpret_cast<const uint4*>(base);
+        for (int i = lane; i < prm.stage_bytes / 16; i += 32) s1[i] = d1[i];
         uint4* sl = reinterpret_cast<uint4*>(g_lat);
         const uint4* dl = reinterpret_cast<const uint4*>(lat);
         for (int i = lane; i < prm.lat_stride / 16; i += 32) sl[i] = dl[i];

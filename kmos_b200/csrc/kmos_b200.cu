@@ -41,6 +41,8 @@ struct kmos_b200_model {
     int max_off[3];  // largest |offset| per axis in the device tables
 };
 
+typedef void (*kb_smem_fn)(const KbSmemParams);
+
 struct kmos_b200_batch {
     kmos_b200_model* model;
     int R, device;
@@ -68,7 +70,8 @@ struct kmos_b200_batch {
     // kernel choice
     int kernel;  // KMOS_B200_KERNEL_GENERIC / SMEM
     KbSmemParams sp;
-    int wpc, ctas_per_sm, sm_count, smem_bytes, ppl, ncond;
+    int wpc, ctas_per_sm, sm_count, smem_bytes, ppl, ncond, regs;
+    kb_smem_fn fn;
     bool smem_ok;
     std::string smem_reason;
 };
@@ -241,6 +244,25 @@ static bool magic_ok(uint32_t magic, int d, int limit) {
     return true;
 }
 
+template <int PPL, int NC>
+static kb_smem_fn kb_pick2(bool split, bool p1g) {
+    if (split) return p1g ? kb_smem_kernel<PPL, NC, true, true> : kb_smem_kernel<PPL, NC, true, false>;
+    return p1g ? kb_smem_kernel<PPL, NC, false, true> : kb_smem_kernel<PPL, NC, false, false>;
+}
+template <int PPL>
+static kb_smem_fn kb_pick1(int nc, bool split, bool p1g) {
+    switch (nc) {
+    case 0: return kb_pick2<PPL, 0>(split, p1g);
+    case 1: return kb_pick2<PPL, 1>(split, p1g);
+    case 2: return kb_pick2<PPL, 2>(split, p1g);
+    case 3: return kb_pick2<PPL, 3>(split, p1g);
+    default: return kb_pick2<PPL, 4>(split, p1g);
+    }
+}
+static kb_smem_fn kb_pick(int ppl, int nc, bool split, bool p1g) {
+    return ppl == 2 ? kb_pick1<2>(nc, split, p1g) : kb_pick1<1>(nc, split, p1g);
+}
+
 // choose the shared-memory configuration; sets b->smem_ok / smem_reason
 static void plan_smem(kmos_b200_batch* b) {
     const kmos_b200_model* m = b->model;
@@ -272,34 +294,62 @@ static void plan_smem(kmos_b200_batch* b) {
     sp.lat_stride = b->lat_stride;
     const size_t p1_bytes = sp.split ? (size_t)sp.n_arenas * sp.cap : (size_t)sp.n_arenas * sp.cap * 2;
     sp.off_hi = (int)p1_bytes;
-    sp.off_p2 = (int)align_up(p1_bytes + (sp.split ? (size_t)sp.n_arenas * sp.cap / 8 : 0), 4);
+    sp.off_p2 = (int)align_up(p1_bytes + (sp.split ? (size_t)sp.n_arenas * sp.cap / 8 : 0), 16);
     sp.img_bytes = (int)align_up((size_t)sp.off_p2 + (size_t)sp.n_classes * b->g.ncells * 2, 16);
-    sp.off_lat = sp.img_bytes;
-    sp.off_ns = sp.off_lat + sp.lat_stride;
-    sp.off_prod = (int)align_up((size_t)sp.off_ns + 4 * m->h.n_proc, 16);
-    sp.off_mbar = sp.off_prod + 8 * 128;  // two zero-prefixed product buffers (kb_smem.cuh)
-    sp.rep_bytes = (int)align_up((size_t)sp.off_mbar + 16, 128);
-    int best_w = 0, best_c = 0, best_total = 0;
-    for (int w = 1; w <= 16; ++w) {
-        int bytes = sp.tab_bytes + w * sp.rep_bytes;
-        if (bytes > max_smem) break;
-        int c = per_sm / (bytes + 1024);  // 1 KB/CTA reserved by the driver
-        if (c > 32) c = 32;
-        if (c * w > 64) c = 64 / w;
-        if (c < 1) continue;
-        if (c * w >= best_total) { best_total = c * w; best_w = w; best_c = c; }  // ties: fewer table copies
-    }
-    if (!best_w) { b->smem_reason = "one replica does not fit in shared memory"; return; }
-    const char* wenv = getenv("KMOS_B200_WARPS_PER_CTA");
-    if (wenv && atoi(wenv) > 0 && sp.tab_bytes + atoi(wenv) * sp.rep_bytes <= max_smem) {
-        best_w = atoi(wenv);
-        best_c = per_sm / (sp.tab_bytes + best_w * sp.rep_bytes + 1024);
-        if (best_c < 1) best_c = 1;
-    }
-    b->wpc = best_w; b->ctas_per_sm = best_c; b->smem_bytes = sp.tab_bytes + best_w * sp.rep_bytes;
     b->ppl = m->h.n_proc > 32 ? 2 : 1;
     b->ncond = d[14];
     if (b->ncond > 4) { b->smem_reason = "more than 4 probes per add"; return; }
+    // two placements of plane 1: with the rest of the image in shared memory, or left in HBM/L2
+    const char* p1env = getenv("KMOS_B200_P1");
+    int best_total = 0;
+    for (int p1g = 0; p1g <= 1; ++p1g) {
+        if (p1env && ((p1env[0] == 's' && p1g == 1) || (p1env[0] == 'g' && p1g == 0))) continue;
+        const int stage_off = p1g ? sp.off_p2 : 0;
+        const int stage_bytes = sp.img_bytes - stage_off;
+        const int sm_p2 = p1g ? 0 : sp.off_p2;
+        const int sm_lat = stage_bytes;
+        const int sm_ns = sm_lat + sp.lat_stride;
+        const int sm_prod = (int)align_up((size_t)sm_ns + 4 * m->h.n_proc, 16);
+        const int sm_mbar = sm_prod + 8 * 128;  // two zero-prefixed product buffers (kb_smem.cuh)
+        const int rep_bytes = (int)align_up((size_t)sm_mbar + 16, 128);
+        cudaFuncAttributes fa;
+        kb_smem_fn fn = kb_pick(b->ppl, b->ncond, sp.split != 0, p1g != 0);
+        if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { cudaGetLastError(); continue; }
+        const int regs = (fa.numRegs + 7) & ~7;
+        int w_regs = prop.regsPerMultiprocessor / (32 * regs);
+        if (w_regs > 32) w_regs = 32;  // 1024 threads per CTA
+        int cand_w = 0, cand_c = 0;
+        for (int w = 1; w <= w_regs; ++w) {
+            int bytes = sp.tab_bytes + w * rep_bytes;
+            if (bytes > max_smem) break;
+            int c = per_sm / (bytes + 1024);  // 1 KB/CTA reserved by the driver
+            if (c > 32) c = 32;
+            if (c * w > 64) c = 64 / w;
+            if (c * w > w_regs) c = w_regs / w;
+            if (c < 1) continue;
+            if (c * w >= cand_w * cand_c) { cand_w = w; cand_c = c; }  // ties: fewer table copies
+        }
+        // keeping the lists in shared memory is the lower-latency choice: prefer it unless leaving them in
+        // L2 buys at least 30 % more resident replicas
+        const int total = cand_w * cand_c;
+        const bool better = p1g ? (total * 10 >= best_total * 13) : (total > best_total);
+        if (total > 0 && (best_total == 0 || better)) {
+            best_total = total;
+            b->wpc = cand_w; b->ctas_per_sm = cand_c; b->smem_bytes = sp.tab_bytes + cand_w * rep_bytes;
+            b->fn = fn; b->regs = fa.numRegs;
+            sp.p1_global = p1g; sp.stage_off = stage_off; sp.stage_bytes = stage_bytes;
+            sp.sm_p2 = sm_p2; sp.sm_lat = sm_lat; sp.sm_ns = sm_ns; sp.sm_prod = sm_prod; sp.sm_mbar = sm_mbar;
+            sp.rep_bytes = rep_bytes;
+        }
+    }
+    if (!best_total) { b->smem_reason = "one replica does not fit in shared memory"; return; }
+    const char* wenv = getenv("KMOS_B200_WARPS_PER_CTA");
+    if (wenv && atoi(wenv) > 0 && sp.tab_bytes + atoi(wenv) * sp.rep_bytes <= max_smem) {
+        b->wpc = atoi(wenv);
+        b->ctas_per_sm = per_sm / (sp.tab_bytes + b->wpc * sp.rep_bytes + 1024);
+        if (b->ctas_per_sm < 1) b->ctas_per_sm = 1;
+        b->smem_bytes = sp.tab_bytes + b->wpc * sp.rep_bytes;
+    }
     int Lx = b->g.size[0], LxLy = b->g.size[0] * b->g.size[1];
     if (Lx == 1 || LxLy == 1) { b->smem_reason = "degenerate lattice"; return; }
     sp.magic_x = (uint32_t)((0x100000000ull / (uint64_t)Lx) + 1);
@@ -405,12 +455,13 @@ extern "C" int kmos_b200_select_kernel(kmos_b200_batch* b, int32_t kind) {
     return KMOS_B200_OK;
 }
 
-extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[8]) {
-    memset(info, 0, 8 * sizeof(int64_t));
+extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[12]) {
+    memset(info, 0, 12 * sizeof(int64_t));
     info[0] = b->kernel;
     if (b->kernel == KMOS_B200_KERNEL_SMEM) {
         info[1] = b->wpc; info[2] = b->smem_bytes; info[3] = b->ctas_per_sm; info[4] = b->sm_count;
         info[5] = b->sp.rep_bytes; info[6] = (int64_t)b->sp.dev_words * 4; info[7] = (b->R + b->wpc - 1) / b->wpc;
+        info[8] = b->sp.p1_global; info[9] = b->regs; info[10] = b->sp.split; info[11] = b->sp.img_bytes;
     } else {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, b->device) == cudaSuccess) info[4] = prop.multiProcessorCount;
@@ -588,27 +639,8 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     sp.nsteps = n;
     const int threads = b->wpc * 32;
     const int blocks = (b->R + b->wpc - 1) / b->wpc;
-#define KB_LAUNCH_S(PPL, NC, SPL)                                                                                          \
-    do {                                                                                                                   \
-        CU(cudaFuncSetAttribute(kb_smem_kernel<PPL, NC, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes)); \
-        kb_smem_kernel<PPL, NC, SPL><<<blocks, threads, b->smem_bytes, b->stream>>>(sp);                                   \
-    } while (0)
-#define KB_LAUNCH(PPL, NC)                                             \
-    do {                                                               \
-        if (sp.split) KB_LAUNCH_S(PPL, NC, true); else KB_LAUNCH_S(PPL, NC, false); \
-    } while (0)
-#define KB_LAUNCH_NC(PPL)                  \
-    switch (b->ncond) {                    \
-    case 0: KB_LAUNCH(PPL, 0); break;      \
-    case 1: KB_LAUNCH(PPL, 1); break;      \
-    case 2: KB_LAUNCH(PPL, 2); break;      \
-    case 3: KB_LAUNCH(PPL, 3); break;      \
-    default: KB_LAUNCH(PPL, 4); break;     \
-    }
-    if (b->ppl == 2) { KB_LAUNCH_NC(2) } else { KB_LAUNCH_NC(1) }
-#undef KB_LAUNCH_NC
-#undef KB_LAUNCH
-#undef KB_LAUNCH_S
+    CU(cudaFuncSetAttribute(b->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+    b->fn<<<blocks, threads, b->smem_bytes, b->stream>>>(sp);
     CU(cudaGetLastError());
     return KMOS_B200_OK;
 }

@@ -203,23 +203,29 @@ def schedule_rounds(ops, lists_of, entry_of):
 
     Ordering that must be kept from the reference's textual order:
       * ops on the same process list (``lists_of(op)``: its nr_of_sites counter and list) -- always;
-      * ops on the same class entry (``entry_of(op)``: exclusivity class x anchor cell) -- only across
-        *groups*.  A group is the guarded-del block or the if-tree add block of one action; within a
-        group at most one op can fire on a given entry (one member of an exclusivity class is registered
-        on a cell / can become available on it), so its ops need no mutual order.
+      * on one class entry (``entry_of(op)``: exclusivity class x anchor cell) an ADD must follow every
+        earlier guarded del of an earlier group (the del that frees the entry for it).
+    Nothing else: at most one member of a class is registered on a cell, so
+      - guarded dels of different processes on one entry: at most one fires, the others only read;
+      - adds of one group (one action's if-tree) on one entry: at most one can fire;
+      - a guarded del of q after an add of q' != q: if the add fired the entry was free before it and holds
+        q' after it -- the del is a no-op either way; if it did not fire they do not interact;
+      - two adds of different groups can both fire only with a del of the first process in between, which is
+        ordered after the first add by its list and before the second add by the rule above.
     """
     rounds = []
     last_list = {}
-    entry_groups = {}  # entry -> {group: last round}
+    entry_dels = {}  # entry -> {group: last round of a guarded del}
     for i, op in enumerate(ops):
-        group = op[4]
+        kind, group = op[0], op[4]
         r = -1
         for x in lists_of(op):
             r = max(r, last_list.get(x, -1))
-        eg = entry_groups.setdefault(entry_of(op), {})
-        for g, rr in eg.items():
-            if g != group:
-                r = max(r, rr)
+        ed = entry_dels.setdefault(entry_of(op), {})
+        if kind == KIND_ADD:
+            for g, rr in ed.items():
+                if g < group:
+                    r = max(r, rr)
         r += 1
         while True:
             if r == len(rounds):
@@ -230,7 +236,8 @@ def schedule_rounds(ops, lists_of, entry_of):
         rounds[r].append(i)
         for x in lists_of(op):
             last_list[x] = r
-        eg[group] = max(eg.get(group, -1), r)
+        if kind == KIND_DEL_IF:
+            ed[group] = max(ed.get(group, -1), r)
     return rounds
 
 

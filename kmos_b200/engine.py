@@ -77,10 +77,11 @@ class Batch(object):
         capi.check(self.L.kmos_b200_select_kernel(self.h, int(kind)))
 
     def kernel_info(self):
-        info = np.zeros(8, dtype=np.int64)
+        info = np.zeros(12, dtype=np.int64)
         capi.check(self.L.kmos_b200_kernel_info(self.h, info))
         keys = ("kernel", "replicas_per_cta", "smem_bytes_per_cta", "ctas_per_sm", "sm_count",
-                "state_bytes_per_replica", "table_bytes", "grid")
+                "state_bytes_per_replica", "table_bytes", "grid", "lists_in_l2", "registers", "split_lists",
+                "image_bytes_per_replica")
         d = dict(zip(keys, (int(x) for x in info)))
         d["kernel_name"] = {capi.KERNEL_GENERIC: "generic", capi.KERNEL_SMEM: "smem"}[d["kernel"]]
         return d
