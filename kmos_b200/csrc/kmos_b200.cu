@@ -315,17 +315,19 @@ static void plan_smem(kmos_b200_batch* b) {
         cudaFuncAttributes fa;
         kb_smem_fn fn = kb_pick(b->ppl, b->ncond, sp.split != 0, p1g != 0);
         if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { cudaGetLastError(); continue; }
+        // registers are allocated per warp in units of 8 per thread and per CTA in groups of 4 warps
         const int regs = (fa.numRegs + 7) & ~7;
-        int w_regs = prop.regsPerMultiprocessor / (32 * regs);
-        if (w_regs > 32) w_regs = 32;  // 1024 threads per CTA
+        const int reg_warps = prop.regsPerMultiprocessor / (32 * regs);  // warps an SM can hold
         int cand_w = 0, cand_c = 0;
-        for (int w = 1; w <= w_regs; ++w) {
+        for (int w = 1; w <= 32; ++w) {
+            const int w4 = (w + 3) & ~3;
+            if (w4 > reg_warps) break;
             int bytes = sp.tab_bytes + w * rep_bytes;
             if (bytes > max_smem) break;
             int c = per_sm / (bytes + 1024);  // 1 KB/CTA reserved by the driver
             if (c > 32) c = 32;
             if (c * w > 64) c = 64 / w;
-            if (c * w > w_regs) c = w_regs / w;
+            if (c * w4 > reg_warps) c = reg_warps / w4;
             if (c < 1) continue;
             if (c * w >= cand_w * cand_c) { cand_w = w; cand_c = c; }  // ties: fewer table copies
         }
