@@ -262,7 +262,7 @@ struct KbCellCtx {
 
 // PPL: processes per lane (1: P <= 32, 2: P <= 64);  NCOND: largest number of dynamic probes of an add
 template <int PPL, int NCOND, bool SPLIT, bool P1G>
-__global__ void kb_smem_kernel(const KbSmemParams prm) {
+__global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemParams prm) {
     extern __shared__ __align__(128) unsigned char kb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
