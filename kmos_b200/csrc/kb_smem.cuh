@@ -452,6 +452,15 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
             const int ca = __shfl_sync(KB_FULL, nb, (int)((h >> 4) & 31u));
             bool ok = valid;
             const int ncond = (int)((h >> 1) & 7u);
+            const int q = (int)((h >> 9) & 63u), cls = (int)((h >> 15) & 31u);
+            const uint32_t member = (h >> 20) & 7u;
+            const int arena = (int)((h >> 23) & 63u), dir = (int)((h >> 29) & 1u);
+            // this lane is the only one touching list q in this round: its length can be read up front, and
+            // when the lists live in L2 the element a del would move is requested before the probes so that
+            // the round trip overlaps them (speculative: harmless if the del does not fire)
+            const int nq = valid ? nS[q] : 0;
+            int last = 0;
+            if (P1G && valid && !(h & 1u) && nq > 0) last = kb_p1_get<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, nq - 1));
 #pragma unroll
             for (int j = 0; j < NCOND; ++j) {
                 const uint32_t cw = (valid && j < ncond) ? ops[(ops_start + i) * STRIDE + 1 + j] : 0u;
@@ -462,12 +471,8 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
                 }
             }
             if (ok) {
-                const int q = (int)((h >> 9) & 63u), cls = (int)((h >> 15) & 31u);
-                const uint32_t member = (h >> 20) & 7u;
-                const int arena = (int)((h >> 23) & 63u), dir = (int)((h >> 29) & 1u);
                 uint16_t* entry = p2 + cls * C;
                 if (h & 1u) {  // add_proc (base.mpy:268-302)
-                    const int nq = nS[q];
                     if (nq >= C || entry[ca] != 0) {
                         status = KB_CAPACITY;
                     } else {
@@ -479,8 +484,7 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
                     const uint32_t e = entry[ca];
                     if ((e >> KB_POS_BITS) == member) {
                         const int pos = (int)(e & KB_POS_MASK);
-                        const int nq = nS[q];
-                        const int last = kb_p1_get<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, nq - 1));
+                        if (!P1G) last = kb_p1_get<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, nq - 1));
                         if (pos < nq) {
                             kb_p1_set<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, pos - 1), last);
                             entry[last] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)pos);

@@ -11,6 +11,7 @@
 //   scalars  KbScalars[R]     kmc_time, kmc_time_step, kmc_step, Philox key/replica id, status, error tuple
 //   otf only: rates_matrix double [R][P][ncells+1], accum_proc double [R][ncells], lut double [R][lut]
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -284,67 +285,69 @@ static void plan_smem(kmos_b200_batch* b) {
     sp.dev_words = m->h.dev_len;
     sp.tab_bytes = (int)align_up((size_t)sp.dev_words * 4, 128);
     sp.n_classes = d[10]; sp.n_arenas = d[11];
-    // spare slots: the two lists of an arena may overshoot ncells transiently by at most the adds of one
-    // event (devtables.py).  Split storage additionally keeps the lists >= 8 slots apart so that no byte of
-    // the bit-8 bitmap is shared between two lists.
-    const char* ns_env = getenv("KMOS_B200_NO_SPLIT");
-    sp.split = (b->g.ncells <= 512 && !(ns_env && ns_env[0] == '1')) ? 1 : 0;
-    sp.cap = sp.split ? (int)align_up((size_t)b->g.ncells + d[15] + 8, 8) : (b->g.ncells + d[15] + 1) & ~1;
     sp.plane_bytes = (int)b->plane_bytes;
     sp.lat_stride = b->lat_stride;
-    const size_t p1_bytes = sp.split ? (size_t)sp.n_arenas * sp.cap : (size_t)sp.n_arenas * sp.cap * 2;
-    sp.off_hi = (int)p1_bytes;
-    sp.off_p2 = (int)align_up(p1_bytes + (sp.split ? (size_t)sp.n_arenas * sp.cap / 8 : 0), 16);
-    sp.img_bytes = (int)align_up((size_t)sp.off_p2 + (size_t)sp.n_classes * b->g.ncells * 2, 16);
     b->ppl = m->h.n_proc > 32 ? 2 : 1;
     b->ncond = d[14];
     if (b->ncond > 4) { b->smem_reason = "more than 4 probes per add"; return; }
-    // two placements of plane 1: with the rest of the image in shared memory, or left in HBM/L2
+    // Two placements of plane 1 (the lists): with the rest of the image in shared memory, or left in HBM/L2.
+    // spare slots: the two lists of an arena may overshoot ncells transiently by at most the adds of one
+    // event (devtables.py).  Split storage (shared-memory placement, <= 512 cells) additionally keeps the
+    // lists >= 8 slots apart so that no byte of the bit-8 bitmap is shared between two lists.
     const char* p1env = getenv("KMOS_B200_P1");
+    const char* ns_env = getenv("KMOS_B200_NO_SPLIT");
     int best_total = 0;
+    double best_score = 0;
+    KbSmemParams best = sp;
     for (int p1g = 0; p1g <= 1; ++p1g) {
         if (p1env && ((p1env[0] == 's' && p1g == 1) || (p1env[0] == 'g' && p1g == 0))) continue;
-        const int stage_off = p1g ? sp.off_p2 : 0;
-        const int stage_bytes = sp.img_bytes - stage_off;
-        const int sm_p2 = p1g ? 0 : sp.off_p2;
-        const int sm_lat = stage_bytes;
-        const int sm_ns = sm_lat + sp.lat_stride;
-        const int sm_prod = (int)align_up((size_t)sm_ns + 4 * m->h.n_proc, 16);
-        const int sm_mbar = sm_prod + 8 * 128;  // two zero-prefixed product buffers (kb_smem.cuh)
-        const int rep_bytes = (int)align_up((size_t)sm_mbar + 16, 128);
+        KbSmemParams c = sp;
+        c.p1_global = p1g;
+        c.split = (!p1g && b->g.ncells <= 512 && !(ns_env && ns_env[0] == '1')) ? 1 : 0;
+        c.cap = c.split ? (int)align_up((size_t)b->g.ncells + d[15] + 8, 8) : (b->g.ncells + d[15] + 1) & ~1;
+        const size_t p1_bytes = c.split ? (size_t)c.n_arenas * c.cap : (size_t)c.n_arenas * c.cap * 2;
+        c.off_hi = (int)p1_bytes;
+        c.off_p2 = (int)align_up(p1_bytes + (c.split ? (size_t)c.n_arenas * c.cap / 8 : 0), 16);
+        c.img_bytes = (int)align_up((size_t)c.off_p2 + (size_t)c.n_classes * b->g.ncells * 2, 16);
+        c.stage_off = p1g ? c.off_p2 : 0;
+        c.stage_bytes = c.img_bytes - c.stage_off;
+        c.sm_p2 = p1g ? 0 : c.off_p2;
+        c.sm_lat = c.stage_bytes;
+        c.sm_ns = c.sm_lat + c.lat_stride;
+        c.sm_prod = (int)align_up((size_t)c.sm_ns + 4 * m->h.n_proc, 16);
+        c.sm_mbar = c.sm_prod + 8 * 128;  // two zero-prefixed product buffers (kb_smem.cuh)
+        c.rep_bytes = (int)align_up((size_t)c.sm_mbar + 16, 128);
         cudaFuncAttributes fa;
-        kb_smem_fn fn = kb_pick(b->ppl, b->ncond, sp.split != 0, p1g != 0);
+        kb_smem_fn fn = kb_pick(b->ppl, b->ncond, c.split != 0, p1g != 0);
         if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { cudaGetLastError(); continue; }
         // registers are allocated per warp in units of 8 per thread and per CTA in groups of 4 warps
         const int regs = (fa.numRegs + 7) & ~7;
         const int reg_warps = prop.regsPerMultiprocessor / (32 * regs);  // warps an SM can hold
-        int cand_w = 0, cand_c = 0;
-        for (int w = 1; w <= 32; ++w) {
+        const int max_threads = fa.maxThreadsPerBlock;
+        for (int w = 1; w <= 32 && w * 32 <= max_threads; ++w) {
             const int w4 = (w + 3) & ~3;
             if (w4 > reg_warps) break;
-            int bytes = sp.tab_bytes + w * rep_bytes;
+            int bytes = c.tab_bytes + w * c.rep_bytes;
             if (bytes > max_smem) break;
-            int c = per_sm / (bytes + 1024);  // 1 KB/CTA reserved by the driver
-            if (c > 32) c = 32;
-            if (c * w > 64) c = 64 / w;
-            if (c * w4 > reg_warps) c = reg_warps / w4;
-            if (c < 1) continue;
-            if (c * w >= cand_w * cand_c) { cand_w = w; cand_c = c; }  // ties: fewer table copies
-        }
-        // keeping the lists in shared memory is the lower-latency choice: prefer it unless leaving them in
-        // L2 buys at least 30 % more resident replicas
-        const int total = cand_w * cand_c;
-        const bool better = p1g ? (total * 10 >= best_total * 13) : (total > best_total);
-        if (total > 0 && (best_total == 0 || better)) {
-            best_total = total;
-            b->wpc = cand_w; b->ctas_per_sm = cand_c; b->smem_bytes = sp.tab_bytes + cand_w * rep_bytes;
-            b->fn = fn; b->regs = fa.numRegs;
-            sp.p1_global = p1g; sp.stage_off = stage_off; sp.stage_bytes = stage_bytes;
-            sp.sm_p2 = sm_p2; sp.sm_lat = sm_lat; sp.sm_ns = sm_ns; sp.sm_prod = sm_prod; sp.sm_mbar = sm_mbar;
-            sp.rep_bytes = rep_bytes;
+            int n = per_sm / (bytes + 1024);  // 1 KB/CTA reserved by the driver
+            if (n > 32) n = 32;
+            if (n * w > 64) n = 64 / w;
+            if (n * w4 > reg_warps) n = reg_warps / w4;
+            if (n < 1) continue;
+            // score: resident replicas per SM x how full the last wave of this batch is; the lists-in-L2
+            // placement pays ~1.5x more latency per step, so it must bring that many more replicas
+            const double waves = (double)b->R / ((double)prop.multiProcessorCount * n * w);
+            const double eff = waves / ceil(waves);
+            const double score = n * w * eff / (p1g ? 1.5 : 1.0);
+            if (score > best_score * 1.0001 || (score > best_score * 0.9999 && n * w < best_total)) {
+                best_score = score; best_total = n * w; best = c;
+                b->wpc = w; b->ctas_per_sm = n; b->smem_bytes = c.tab_bytes + w * c.rep_bytes;
+                b->fn = fn; b->regs = fa.numRegs;
+            }
         }
     }
     if (!best_total) { b->smem_reason = "one replica does not fit in shared memory"; return; }
+    sp = best;
     const char* wenv = getenv("KMOS_B200_WARPS_PER_CTA");
     if (wenv && atoi(wenv) > 0 && sp.tab_bytes + atoi(wenv) * sp.rep_bytes <= max_smem) {
         b->wpc = atoi(wenv);
