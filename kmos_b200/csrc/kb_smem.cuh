@@ -460,7 +460,10 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
             // the round trip overlaps them (speculative: harmless if the del does not fire)
             const int nq = valid ? nS[q] : 0;
             int last = 0;
-            if (P1G && valid && !(h & 1u) && nq > 0) last = kb_p1_get<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, nq - 1));
+            if (P1G) {  // unconditional load from an always-valid slot: nothing consumes it before the del body
+                const bool want = valid && !(h & 1u) && nq > 0;
+                last = kb_p1_get<SPLIT>(p1, p1hi, want ? kb_slot(arena, dir, cap, nq - 1) : 0);
+            }
 #pragma unroll
             for (int j = 0; j < NCOND; ++j) {
                 const uint32_t cw = (valid && j < ncond) ? ops[(ops_start + i) * STRIDE + 1 + j] : 0u;
