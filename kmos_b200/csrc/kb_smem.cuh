@@ -39,8 +39,9 @@ struct KbScalars {
 
 struct KbSmemParams {
     // model / geometry
-    const int32_t* dev;  // SEC_DEVICE in global memory
+    const int32_t* dev;  // lane tables in global memory: SEC_DEVICE with ops specialised for this geometry
     int dev_words;
+    int nbt_bytes;       // bytes of the per-CTA neighbour table (0: compute neighbours arithmetically)
     int n_proc, spuck, dim;
     int size[3];
     int ncells, volume;
@@ -261,7 +262,11 @@ struct KbCellCtx {
 };
 
 // PPL: processes per lane (1: P <= 32, 2: P <= 64);  NCOND: largest number of dynamic probes of an add
-template <int PPL, int NCOND, bool SPLIT, bool P1G>
+// Specialised op (host: specialise_tables in kmos_b200.cu): 2 + NCOND words
+//   w0 = kind | ncond<<1 | off_id<<4 | q<<9 | member<<15 | dir<<18
+//   w1 = class base (cls * ncells) | first slot of the list (arena*cap, or arena*cap + cap-1 if it grows down) << 16
+//   then ncond probe words off_id | n<<5 | mask<<8
+template <int PPL, int NCOND, bool SPLIT, bool P1G, bool NBT>
 __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemParams prm) {
     extern __shared__ __align__(128) unsigned char kb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -269,17 +274,30 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
     int32_t* tab = reinterpret_cast<int32_t*>(kb_smem);
     for (int i = threadIdx.x; i < prm.dev_words; i += blockDim.x) tab[i] = prm.dev[i];
     __syncthreads();
-    const int rep = blockIdx.x * wpc + warp;
-    if (rep >= prm.R) return;  // no block-wide barrier below this line
-
     const uint4* events = reinterpret_cast<const uint4*>(tab + tab[3]);
     const uint32_t* ops = reinterpret_cast<const uint32_t*>(tab + tab[4]);
     const uint32_t* offsets = reinterpret_cast<const uint32_t*>(tab + tab[7]);
     const uint32_t* procinfo = reinterpret_cast<const uint32_t*>(tab + tab[9]);
     const int n_off = tab[8];
-    constexpr int STRIDE = 1 + NCOND;
+    constexpr int STRIDE = 2 + NCOND;
 
-    unsigned char* base = kb_smem + prm.tab_bytes + (size_t)warp * prm.rep_bytes;
+    KbCellCtx cc;
+    cc.Lx = prm.size[0]; cc.Ly = prm.size[1]; cc.Lz = prm.size[2]; cc.dim = prm.dim;
+    cc.magic_x = prm.magic_x; cc.magic_xy = prm.magic_xy;
+    // neighbour table shared by the CTA's replicas: nbT[cell][o] = cell index of (cell + offset o)
+    uint16_t* nbT = reinterpret_cast<uint16_t*>(kb_smem + prm.tab_bytes);
+    if (NBT) {
+        for (int idx = threadIdx.x; idx < prm.ncells * n_off; idx += blockDim.x) {
+            const int c = idx / n_off;
+            cc.decode(c);
+            nbT[idx] = (uint16_t)cc.cell_at(offsets[idx - c * n_off]);
+        }
+        __syncthreads();
+    }
+    const int rep = blockIdx.x * wpc + warp;
+    if (rep >= prm.R) return;  // no block-wide barrier below this line
+
+    unsigned char* base = kb_smem + prm.tab_bytes + prm.nbt_bytes + (size_t)warp * prm.rep_bytes;
     uint16_t* p2 = reinterpret_cast<uint16_t*>(base + prm.sm_p2);
     uint8_t* lat = base + prm.sm_lat;
     int32_t* nS = reinterpret_cast<int32_t*>(base + prm.sm_ns);
@@ -337,9 +355,6 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
     int status = sc.status;
     int err0 = 0, err1 = 0, err2 = 0, err3 = 0, err4 = 0;
 
-    KbCellCtx cc;
-    cc.Lx = prm.size[0]; cc.Ly = prm.size[1]; cc.Lz = prm.size[2]; cc.dim = prm.dim;
-    cc.magic_x = prm.magic_x; cc.magic_xy = prm.magic_xy;
     const uint32_t k0 = (uint32_t)sc.seed, k1 = (uint32_t)(sc.seed >> 32);
     const uint32_t my_off = lane < n_off ? offsets[lane] : 0u;
     const int len1 = min(P, 32), len2 = max(P - 32, 0);
@@ -426,8 +441,13 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
         // -- run_proc_nr(pidx+1, site): lattice writes, then rounds of list operations
         const uint4 eh = events[2 * pidx], ew = events[2 * pidx + 1];
         const int ops_start = (int)(eh.x & 0xFFFFu), n_rounds = (int)((eh.x >> 16) & 15u), n_writes = (int)((eh.x >> 20) & 15u);
-        cc.decode(cell);
-        const int nb = cc.cell_at(my_off);  // lane l: cell index of neighbour offset l
+        int nb;  // lane l: cell index of neighbour offset l
+        if (NBT) {
+            nb = lane < n_off ? (int)nbT[cell * n_off + lane] : 0;
+        } else {
+            cc.decode(cell);
+            nb = cc.cell_at(my_off);
+        }
         {
             const uint32_t w = lane == 0 ? ew.x : (lane == 1 ? ew.y : (lane == 2 ? ew.z : ew.w));
             const int wcell = __shfl_sync(KB_FULL, nb, (int)(w & 31u));
@@ -448,13 +468,17 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
             const int endr = (int)((ends >> (8 * r)) & 255u);
             const int i = start + lane;
             const bool valid = i < endr;
-            const uint32_t h = valid ? ops[(ops_start + i) * STRIDE] : 0u;
+            const uint32_t* op = ops + (ops_start + i) * STRIDE;
+            const uint32_t h = valid ? op[0] : 0u;
+            const uint32_t h1 = valid ? op[1] : 0u;
             const int ca = __shfl_sync(KB_FULL, nb, (int)((h >> 4) & 31u));
             bool ok = valid;
             const int ncond = (int)((h >> 1) & 7u);
-            const int q = (int)((h >> 9) & 63u), cls = (int)((h >> 15) & 31u);
-            const uint32_t member = (h >> 20) & 7u;
-            const int arena = (int)((h >> 23) & 63u), dir = (int)((h >> 29) & 1u);
+            const int q = (int)((h >> 9) & 63u);
+            const uint32_t member = (h >> 15) & 7u;
+            const bool down = (h >> 18) & 1u;
+            const int slot0 = (int)(h1 >> 16);
+            uint16_t* entry = p2 + (h1 & 0xFFFFu);
             // this lane is the only one touching list q in this round: its length can be read up front, and
             // when the lists live in L2 the element a del would move is requested before the probes so that
             // the round trip overlaps them (speculative: harmless if the del does not fire)
@@ -462,11 +486,11 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
             int last = 0;
             if (P1G) {  // unconditional load from an always-valid slot: nothing consumes it before the del body
                 const bool want = valid && !(h & 1u) && nq > 0;
-                last = kb_p1_get<SPLIT>(p1, p1hi, want ? kb_slot(arena, dir, cap, nq - 1) : 0);
+                last = kb_p1_get<SPLIT>(p1, p1hi, want ? (down ? slot0 - (nq - 1) : slot0 + (nq - 1)) : 0);
             }
 #pragma unroll
             for (int j = 0; j < NCOND; ++j) {
-                const uint32_t cw = (valid && j < ncond) ? ops[(ops_start + i) * STRIDE + 1 + j] : 0u;
+                const uint32_t cw = (valid && j < ncond) ? op[2 + j] : 0u;
                 const int ccell = __shfl_sync(KB_FULL, nb, (int)(cw & 31u));
                 if (valid && j < ncond) {
                     const uint32_t sp = lat[ccell * spuck + (int)((cw >> 5) & 7u) - 1];
@@ -474,12 +498,11 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
                 }
             }
             if (ok) {
-                uint16_t* entry = p2 + cls * C;
                 if (h & 1u) {  // add_proc (base.mpy:268-302)
                     if (nq >= C || entry[ca] != 0) {
                         status = KB_CAPACITY;
                     } else {
-                        kb_p1_set<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, nq), ca);
+                        kb_p1_set<SPLIT>(p1, p1hi, down ? slot0 - nq : slot0 + nq, ca);
                         entry[ca] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)(nq + 1));
                         nS[q] = nq + 1;
                     }
@@ -487,9 +510,9 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
                     const uint32_t e = entry[ca];
                     if ((e >> KB_POS_BITS) == member) {
                         const int pos = (int)(e & KB_POS_MASK);
-                        if (!P1G) last = kb_p1_get<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, nq - 1));
+                        if (!P1G) last = kb_p1_get<SPLIT>(p1, p1hi, down ? slot0 - (nq - 1) : slot0 + (nq - 1));
                         if (pos < nq) {
-                            kb_p1_set<SPLIT>(p1, p1hi, kb_slot(arena, dir, cap, pos - 1), last);
+                            kb_p1_set<SPLIT>(p1, p1hi, down ? slot0 - (pos - 1) : slot0 + (pos - 1), last);
                             entry[last] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)pos);
                         }
                         entry[ca] = 0;

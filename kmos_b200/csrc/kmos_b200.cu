@@ -73,6 +73,8 @@ struct kmos_b200_batch {
     KbSmemParams sp;
     int wpc, ctas_per_sm, sm_count, smem_bytes, ppl, ncond, regs;
     kb_smem_fn fn;
+    std::vector<int32_t> spec;  // lane tables specialised for this geometry (host copy)
+    int32_t* d_spec;
     bool smem_ok;
     std::string smem_reason;
 };
@@ -245,23 +247,58 @@ static bool magic_ok(uint32_t magic, int d, int limit) {
     return true;
 }
 
+template <int PPL, int NC, bool NBT>
+static kb_smem_fn kb_pick3(bool split, bool p1g) {
+    if (split) return p1g ? kb_smem_kernel<PPL, NC, true, true, NBT> : kb_smem_kernel<PPL, NC, true, false, NBT>;
+    return p1g ? kb_smem_kernel<PPL, NC, false, true, NBT> : kb_smem_kernel<PPL, NC, false, false, NBT>;
+}
 template <int PPL, int NC>
-static kb_smem_fn kb_pick2(bool split, bool p1g) {
-    if (split) return p1g ? kb_smem_kernel<PPL, NC, true, true> : kb_smem_kernel<PPL, NC, true, false>;
-    return p1g ? kb_smem_kernel<PPL, NC, false, true> : kb_smem_kernel<PPL, NC, false, false>;
+static kb_smem_fn kb_pick2(bool split, bool p1g, bool nbt) {
+    return nbt ? kb_pick3<PPL, NC, true>(split, p1g) : kb_pick3<PPL, NC, false>(split, p1g);
 }
 template <int PPL>
-static kb_smem_fn kb_pick1(int nc, bool split, bool p1g) {
+static kb_smem_fn kb_pick1(int nc, bool split, bool p1g, bool nbt) {
     switch (nc) {
-    case 0: return kb_pick2<PPL, 0>(split, p1g);
-    case 1: return kb_pick2<PPL, 1>(split, p1g);
-    case 2: return kb_pick2<PPL, 2>(split, p1g);
-    case 3: return kb_pick2<PPL, 3>(split, p1g);
-    default: return kb_pick2<PPL, 4>(split, p1g);
+    case 0: return kb_pick2<PPL, 0>(split, p1g, nbt);
+    case 1: return kb_pick2<PPL, 1>(split, p1g, nbt);
+    case 2: return kb_pick2<PPL, 2>(split, p1g, nbt);
+    case 3: return kb_pick2<PPL, 3>(split, p1g, nbt);
+    default: return kb_pick2<PPL, 4>(split, p1g, nbt);
     }
 }
-static kb_smem_fn kb_pick(int ppl, int nc, bool split, bool p1g) {
-    return ppl == 2 ? kb_pick1<2>(nc, split, p1g) : kb_pick1<1>(nc, split, p1g);
+static kb_smem_fn kb_pick(int ppl, int nc, bool split, bool p1g, bool nbt) {
+    return ppl == 2 ? kb_pick1<2>(nc, split, p1g, nbt) : kb_pick1<1>(nc, split, p1g, nbt);
+}
+
+// Lane tables specialised for one geometry: every op gets a second word with its class base (cls * ncells)
+// and the first slot of its list (arena * cap, or the arena's last slot if the list grows downwards), so the
+// kernel's round body needs no multiplications.  Layout otherwise as written by kmos_b200/devtables.py.
+static bool specialise_tables(const int32_t* d, int ncells, int cap, std::vector<int32_t>* out) {
+    const int n_events = d[2], events_off = d[3], ops_off = d[4], n_ops = d[5], stride = d[6];
+    const int offsets_off = d[7], n_off = d[8], procinfo_off = d[9], n_proc = d[2];
+    const int ev_words = offsets_off - 0;  (void)ev_words;
+    const int new_stride = stride + 1;
+    std::vector<int32_t>& o = *out;
+    o.assign(d, d + ops_off);  // header + events
+    const int new_ops_off = (int)o.size();
+    for (int i = 0; i < n_ops; ++i) {
+        const uint32_t h = (uint32_t)d[ops_off + i * stride];
+        const uint32_t kind = h & 1u, ncond = (h >> 1) & 7u, off_id = (h >> 4) & 31u, q = (h >> 9) & 63u;
+        const uint32_t cls = (h >> 15) & 31u, member = (h >> 20) & 7u, arena = (h >> 23) & 63u, dir = (h >> 29) & 1u;
+        const uint32_t p2base = cls * (uint32_t)ncells;
+        const uint32_t slot0 = arena * (uint32_t)cap + (dir ? (uint32_t)cap - 1u : 0u);
+        if (p2base > 0xFFFFu || slot0 > 0xFFFFu) return false;
+        o.push_back((int32_t)(kind | (ncond << 1) | (off_id << 4) | (q << 9) | (member << 15) | (dir << 18)));
+        o.push_back((int32_t)(p2base | (slot0 << 16)));
+        for (int j = 1; j < stride; ++j) o.push_back(d[ops_off + i * stride + j]);
+    }
+    const int new_offsets_off = (int)o.size();
+    for (int i = 0; i < n_off; ++i) o.push_back(d[offsets_off + i]);
+    const int new_procinfo_off = (int)o.size();
+    for (int i = 0; i < n_proc; ++i) o.push_back(d[procinfo_off + i]);
+    o[4] = new_ops_off; o[6] = new_stride; o[7] = new_offsets_off; o[9] = new_procinfo_off;
+    (void)n_events; (void)events_off;
+    return true;
 }
 
 // choose the shared-memory configuration; sets b->smem_ok / smem_reason
@@ -282,8 +319,12 @@ static void plan_smem(kmos_b200_batch* b) {
     const int32_t* d = m->h.dev;
     KbSmemParams& sp = b->sp;
     memset(&sp, 0, sizeof sp);
-    sp.dev_words = m->h.dev_len;
+    sp.dev_words = m->h.dev_len + d[5];  // specialised ops carry one extra word each
     sp.tab_bytes = (int)align_up((size_t)sp.dev_words * 4, 128);
+    // per-CTA neighbour table (cell x offset -> cell), if it is small next to the replicas it serves
+    const size_t nbt = (size_t)b->g.ncells * d[8] * 2;
+    const char* nbt_env = getenv("KMOS_B200_NO_NBT");
+    sp.nbt_bytes = (nbt <= 16384 && !(nbt_env && nbt_env[0] == '1')) ? (int)align_up(nbt, 128) : 0;
     sp.n_classes = d[10]; sp.n_arenas = d[11];
     sp.plane_bytes = (int)b->plane_bytes;
     sp.lat_stride = b->lat_stride;
@@ -318,7 +359,7 @@ static void plan_smem(kmos_b200_batch* b) {
         c.sm_mbar = c.sm_prod + 8 * 128;  // two zero-prefixed product buffers (kb_smem.cuh)
         c.rep_bytes = (int)align_up((size_t)c.sm_mbar + 16, 128);
         cudaFuncAttributes fa;
-        kb_smem_fn fn = kb_pick(b->ppl, b->ncond, c.split != 0, p1g != 0);
+        kb_smem_fn fn = kb_pick(b->ppl, b->ncond, c.split != 0, p1g != 0, c.nbt_bytes != 0);
         if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { cudaGetLastError(); continue; }
         // registers are allocated per warp in units of 8 per thread and per CTA in groups of 4 warps
         const int regs = (fa.numRegs + 7) & ~7;
@@ -327,7 +368,7 @@ static void plan_smem(kmos_b200_batch* b) {
         for (int w = 1; w <= 32 && w * 32 <= max_threads; ++w) {
             const int w4 = (w + 3) & ~3;
             if (w4 > reg_warps) break;
-            int bytes = c.tab_bytes + w * c.rep_bytes;
+            int bytes = c.tab_bytes + c.nbt_bytes + w * c.rep_bytes;
             if (bytes > max_smem) break;
             int n = per_sm / (bytes + 1024);  // 1 KB/CTA reserved by the driver
             if (n > 32) n = 32;
@@ -341,7 +382,7 @@ static void plan_smem(kmos_b200_batch* b) {
             const double score = n * w * eff / (p1g ? 1.5 : 1.0);
             if (score > best_score * 1.0001 || (score > best_score * 0.9999 && n * w < best_total)) {
                 best_score = score; best_total = n * w; best = c;
-                b->wpc = w; b->ctas_per_sm = n; b->smem_bytes = c.tab_bytes + w * c.rep_bytes;
+                b->wpc = w; b->ctas_per_sm = n; b->smem_bytes = c.tab_bytes + c.nbt_bytes + w * c.rep_bytes;
                 b->fn = fn; b->regs = fa.numRegs;
             }
         }
@@ -349,12 +390,14 @@ static void plan_smem(kmos_b200_batch* b) {
     if (!best_total) { b->smem_reason = "one replica does not fit in shared memory"; return; }
     sp = best;
     const char* wenv = getenv("KMOS_B200_WARPS_PER_CTA");
-    if (wenv && atoi(wenv) > 0 && sp.tab_bytes + atoi(wenv) * sp.rep_bytes <= max_smem) {
+    if (wenv && atoi(wenv) > 0 && sp.tab_bytes + sp.nbt_bytes + atoi(wenv) * sp.rep_bytes <= max_smem) {
         b->wpc = atoi(wenv);
-        b->ctas_per_sm = per_sm / (sp.tab_bytes + b->wpc * sp.rep_bytes + 1024);
+        b->ctas_per_sm = per_sm / (sp.tab_bytes + sp.nbt_bytes + b->wpc * sp.rep_bytes + 1024);
         if (b->ctas_per_sm < 1) b->ctas_per_sm = 1;
-        b->smem_bytes = sp.tab_bytes + b->wpc * sp.rep_bytes;
+        b->smem_bytes = sp.tab_bytes + sp.nbt_bytes + b->wpc * sp.rep_bytes;
     }
+    if (!specialise_tables(d, b->g.ncells, sp.cap, &b->spec)) { b->smem_reason = "class/arena bases exceed 16 bits"; return; }
+    if ((int)b->spec.size() != sp.dev_words) { b->smem_reason = "internal: specialised table size"; return; }
     int Lx = b->g.size[0], LxLy = b->g.size[0] * b->g.size[1];
     if (Lx == 1 || LxLy == 1) { b->smem_reason = "degenerate lattice"; return; }
     sp.magic_x = (uint32_t)((0x100000000ull / (uint64_t)Lx) + 1);
@@ -431,7 +474,12 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     plan_smem(b);
     b->image = nullptr;
     b->compact_valid = false;
-    if (b->smem_ok) CU(cudaMalloc(&b->image, (size_t)R * b->sp.img_bytes));
+    b->d_spec = nullptr;
+    if (b->smem_ok) {
+        CU(cudaMalloc(&b->image, (size_t)R * b->sp.img_bytes));
+        CU(cudaMalloc(&b->d_spec, b->spec.size() * 4));
+        CU(cudaMemcpy(b->d_spec, b->spec.data(), b->spec.size() * 4, cudaMemcpyHostToDevice));
+    }
     b->kernel = b->smem_ok ? KMOS_B200_KERNEL_SMEM : KMOS_B200_KERNEL_GENERIC;
     *out = b;
     return KMOS_B200_OK;
@@ -443,7 +491,7 @@ extern "C" void kmos_b200_batch_destroy(kmos_b200_batch* b) {
     cudaStreamSynchronize(b->stream);
     cudaFree(b->d_blob); cudaFree(b->lattice); cudaFree(b->p1); cudaFree(b->p2); cudaFree(b->nsites);
     cudaFree(b->rates); cudaFree(b->integ); cudaFree(b->accum); cudaFree(b->procstat); cudaFree(b->sc);
-    cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->occ); cudaFree(b->group_of); cudaFree(b->image);
+    cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->occ); cudaFree(b->group_of); cudaFree(b->image); cudaFree(b->d_spec);
     cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
     cudaStreamDestroy(b->own_stream);
     delete b;
@@ -569,7 +617,7 @@ extern "C" int kmos_b200_set_otf_lut(kmos_b200_batch* b, const double* lut) {
 
 static KbSmemParams smem_params(const kmos_b200_batch* b) {
     KbSmemParams sp = b->sp;
-    sp.dev = b->d.dev;
+    sp.dev = b->d_spec;
     sp.lattice = b->lattice; sp.nsites = b->nsites; sp.image = b->image;
     sp.p1 = (uint16_t*)b->p1; sp.p2 = (uint16_t*)b->p2;
     sp.rates = b->rates; sp.integ = b->integ; sp.procstat = b->procstat; sp.sc = b->sc;
