@@ -154,8 +154,6 @@ def test_event_tables_reproduce_avail_order(name, size, steps):
     m = EventModel(blob, info, o)
     m.check(o)
     for i in range(steps):
-        # drive with the oracle's own selection; kmc_step must advance for a fresh Philox draw
-        o.do_steps(0)
         p, s, st = _next(o)
         assert st == oracle.OK
         m.run(p, s)
@@ -164,15 +162,9 @@ def test_event_tables_reproduce_avail_order(name, size, steps):
 
 
 def _next(o):
-    """One full oracle step, returning the (proc, site) it executed."""
-    before = o.procstat
-    lat_before = o.lattice
-    # replay selection with a twin call sequence: get_next_kmc_step would reuse the same Philox counter,
-    # so step once and recover (proc, site) from procstat / the changed sites is ambiguous -> instead use
-    # the documented pair get_next_kmc_step + run_proc_nr, bumping the Philox step via do_steps is not
-    # possible.  We emulate: the oracle draws with counter = kmc_step, which run_proc_nr does not advance,
-    # hence we mix the site into the seed by re-seeding per event.
-    o.L.kmos_oracle_seed(o.h, oracle.RNG_PHILOX, int(before.sum()) * 7919 + 13, 0)
+    """One oracle event through get_next_kmc_step + run_proc_nr, returning the (proc, site) it executed.
+    That pair of calls does not advance kmc_step (the Philox counter), so the key is changed per event."""
+    o.L.kmos_oracle_seed(o.h, oracle.RNG_PHILOX, int(o.procstat.sum()) * 7919 + 13, 0)
     p, s, st = o.get_next_kmc_step()
     if st == oracle.OK:
         o.run_proc_nr(p, s)

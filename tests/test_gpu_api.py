@@ -1,0 +1,63 @@
+"""C-ABI entry points not covered by the parity suites: rate setters/getters, time setter, tallies,
+kernel selection, argument validation."""
+import numpy as np
+import pytest
+
+from conftest import load_model
+from kmos_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rate_setters_tallies_and_validation():
+    from kmos_b200 import engine
+    ir, blob, info = load_model("zgb_local_smart")
+    m = engine.Model(ir=ir, blob=blob, info=info)
+    R = 6
+    rates = np.tile(np.array([0.5, 0.25, 0.25, 1e3, 1e3, 1e3, 1e3, 1e-3, 1e-3, 1e-3]), (R, 1))
+    b = engine.Batch(m, R, [10, 10], rates=rates)
+    assert np.array_equal(b.rates, rates)
+    b.set_rate_const(1, 0.75, replica=2)          # base.set_rate_const(proc, rate) on one replica
+    b.set_rate_const(4, 2e3)                       # broadcast
+    got = b.rates
+    assert got[2, 0] == 0.75 and np.all(got[:, 3] == 2e3) and got[0, 0] == 0.5
+    with pytest.raises(capi.KmosB200Error):
+        b.set_rates(-rates)                        # negative rate constants are rejected
+    with pytest.raises(capi.KmosB200Error):
+        b.set_rate_const(99, 1.0)
+    b.do_steps(300)
+    acc = b.accum_rates                            # base.update_accum_rate + get_accum_rate
+    ns = b.nr_of_sites
+    np.testing.assert_allclose(acc[:, -1], (ns * got).sum(axis=1), rtol=1e-12)
+    # tallies, host path: two groups
+    t = b.split_tally(b.reduce_tallies(np.array([0, 0, 0, 1, 1, 1]), 2))
+    ps = b.procstat
+    assert np.array_equal(t["procstat"][0], ps[:3].sum(axis=0)) and np.array_equal(t["procstat"][1], ps[3:].sum(axis=0))
+    np.testing.assert_allclose(t["kmc_time"], [b.kmc_time[:3].sum(), b.kmc_time[3:].sum()], rtol=1e-14)
+    np.testing.assert_allclose(t["occupation"][0], b.occupation[:3].sum(axis=0).reshape(-1), rtol=1e-14)
+    assert list(t["n_replicas"]) == [3, 3] and list(t["kmc_steps"]) == [900, 900]
+    # base.set_kmc_time
+    capi.check(b.L.kmos_b200_set_kmc_time(b.h, np.zeros(R)))
+    assert np.all(b.kmc_time == 0)
+    b.do_steps(10)
+    assert np.all(b.kmc_time > 0) and np.all(b.kmc_step == 310)
+    b.close()
+
+
+def test_kernel_selection_and_fallback_reasons():
+    from kmos_b200 import engine
+    ir, blob, info = load_model("pairwise_lat_int")
+    m = engine.Model(ir=ir, blob=blob, info=info)
+    b = engine.Batch(m, 2, [8, 8], rates=np.ones((2, 19)))
+    assert b.kernel_info()["kernel_name"] == "generic"
+    with pytest.raises(capi.KmosB200Error, match="shared-memory kernel unavailable"):
+        b.select_kernel(capi.KERNEL_SMEM)
+    b.close()
+    # a lattice smaller than twice the interaction range cannot use the compact class entries
+    ir, blob, info = load_model("zgb_local_smart")
+    m = engine.Model(ir=ir, blob=blob, info=info)
+    b = engine.Batch(m, 2, [2, 2], rates=np.ones((2, 10)))
+    assert b.kernel_info()["kernel_name"] == "generic"
+    b.do_steps(50)
+    assert np.all(b.kmc_step == 50)
+    b.close()

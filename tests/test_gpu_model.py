@@ -93,3 +93,29 @@ def test_configuration_roundtrip_put_and_f2py_shim(tmp_path):
 def o0_total(o):
     o.L.kmos_oracle_update_accum_rate(o.h)
     return float(o.accum_rates[-1])
+
+
+def test_model_runner_writes_reference_shaped_dat(tmp_path):
+    from kmos_b200.runner import ModelRunner, PressureParameter, TemperatureParameter
+
+    class Scan(ModelRunner):
+        T = TemperatureParameter(600)
+        p_COgas = PressureParameter(min=0.5, max=2.0, steps=3)
+        p_O2gas = PressureParameter(1)
+
+    path = os.path.join(GOLDEN, "models", "ab_local_smart.json")
+    out = str(tmp_path / "Scan.dat")
+    runner = Scan(path, size=[10, 10], seeds=2)
+    assert [p["p_COgas"] for p in runner.grid_points()] == pytest.approx([0.5, 1.0, 2.0])
+    header, rows = runner.run(init_steps=2000, sample_steps=4000, samples=2, outfile=out)
+    assert rows.shape == (3, len(header[1:].split()))
+    lines = open(out).read().splitlines()
+    assert lines[0] == header.strip()
+    data = np.loadtxt(out)
+    assert data.shape == rows.shape
+    cols = header[1:].split()
+    np.testing.assert_allclose(data[:, cols.index("p_COgas")], [0.5, 1.0, 2.0], rtol=1e-5)
+    assert np.all(data[:, cols.index("kmc_steps")] == 4000)
+    # coverages of one site type sum to one
+    occ = [c for c in cols if c.endswith("_default_a")]
+    np.testing.assert_allclose(data[:, [cols.index(c) for c in occ]].sum(axis=1), 1.0, rtol=1e-4)
