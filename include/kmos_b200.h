@@ -50,7 +50,8 @@ enum {
 enum {
     KMOS_B200_KERNEL_AUTO = 0,
     KMOS_B200_KERNEL_GENERIC = 1, /* thread-per-replica byte-code engine, state in HBM (all backends) */
-    KMOS_B200_KERNEL_SMEM = 2     /* warp-per-replica, state in shared memory (local_smart that fits) */
+    KMOS_B200_KERNEL_SMEM = 2,    /* warp-per-replica, state in shared memory (local_smart that fits) */
+    KMOS_B200_KERNEL_WARP_HBM = 3 /* warp-per-replica, state in HBM/L2 (lat_int: nli_* decision trees per lane) */
 };
 
 const char *kmos_b200_last_error(void);

@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 OK = 0
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SMEM = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SMEM, KERNEL_WARP_HBM = 0, 1, 2, 3
 REPLICA_OK, REPLICA_DEADLOCK, REPLICA_SPECIES_MISMATCH, REPLICA_CAPACITY, REPLICA_BAD_MODEL = range(5)
 
 
@@ -26,7 +26,7 @@ class KmosB200Error(RuntimeError):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_interp.h", "kb_common.h")] + \
+    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_interp.h", "kb_common.h")] + \
         [os.path.join(os.path.dirname(HERE), "include", "kmos_b200.h")]
 
 

@@ -22,6 +22,7 @@
 #include "../../include/kmos_b200.h"
 #include "kb_interp.h"
 #include "kb_smem.cuh"
+#include "kb_latint.cuh"
 
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
@@ -77,6 +78,9 @@ struct kmos_b200_batch {
     int32_t* d_spec;
     bool smem_ok;
     std::string smem_reason;
+    bool li_ok;  // warp-per-replica lat_int kernel available
+    KbLatintParams li;
+    int li_wpc, li_smem_bytes;
 };
 
 extern "C" const char* kmos_b200_last_error(void) { return g_err.c_str(); }
@@ -301,6 +305,41 @@ static bool specialise_tables(const int32_t* d, int ncells, int cap, std::vector
     return true;
 }
 
+// lat_int: warp-per-replica kernel on the canonical HBM layout
+static void plan_latint(kmos_b200_batch* b) {
+    const kmos_b200_model* m = b->model;
+    b->li_ok = false;
+    const int32_t* d = m->h.dev;
+    if (m->h.backend != KB_BACKEND_LAT_INT || !d || m->h.dev_len < 16 || d[0] != 3 || d[1] != 1) return;
+    if (m->h.n_proc > 64) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, b->device) != cudaSuccess) return;
+    // offsets are applied twice (op cell, then probe inside the decision tree), each |d| <= L
+    for (int i = 0; i < d[8]; ++i) {
+        uint32_t w = (uint32_t)d[d[7] + i];
+        for (int a = 0; a < m->h.dim; ++a)
+            if (abs((int)(int8_t)((w >> (8 * a)) & 255u)) > b->g.size[a]) return;
+    }
+    int Lx = b->g.size[0], LxLy = b->g.size[0] * b->g.size[1];
+    if (Lx == 1 || LxLy == 1) return;
+    KbLatintParams& li = b->li;
+    memset(&li, 0, sizeof li);
+    li.magic_x = (uint32_t)((0x100000000ull / (uint64_t)Lx) + 1);
+    li.magic_xy = (uint32_t)((0x100000000ull / (uint64_t)LxLy) + 1);
+    if (!magic_ok(li.magic_x, Lx, b->g.ncells) || !magic_ok(li.magic_xy, LxLy, b->g.ncells)) return;
+    li.dev_words = m->h.dev_len;
+    li.tab_bytes = (int)align_up((size_t)li.dev_words * 4, 128);
+    li.rep_bytes = 1280;  // nr_of_sites (256 B) + two zero-prefixed product buffers (1 KB)
+    b->li_wpc = 8;
+    b->li_smem_bytes = li.tab_bytes + b->li_wpc * li.rep_bytes;
+    if (b->li_smem_bytes > (int)prop.sharedMemPerBlockOptin) return;
+    li.n_proc = m->h.n_proc; li.n_species = m->h.n_species; li.spuck = m->h.spuck; li.dim = m->h.dim;
+    for (int a = 0; a < 3; ++a) li.size[a] = b->g.size[a];
+    li.ncells = b->g.ncells;
+    b->sm_count = prop.multiProcessorCount;
+    b->li_ok = true;
+}
+
 // choose the shared-memory configuration; sets b->smem_ok / smem_reason
 static void plan_smem(kmos_b200_batch* b) {
     const kmos_b200_model* m = b->model;
@@ -472,6 +511,7 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     CU(cudaMemcpy(b->sc, sc.data(), sc.size() * sizeof(KbScalars), cudaMemcpyHostToDevice));
     b->tally = nullptr; b->occ = nullptr; b->group_of = nullptr; b->tally_groups = 0;
     plan_smem(b);
+    plan_latint(b);
     b->image = nullptr;
     b->compact_valid = false;
     b->d_spec = nullptr;
@@ -480,7 +520,7 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
         CU(cudaMalloc(&b->d_spec, b->spec.size() * 4));
         CU(cudaMemcpy(b->d_spec, b->spec.data(), b->spec.size() * 4, cudaMemcpyHostToDevice));
     }
-    b->kernel = b->smem_ok ? KMOS_B200_KERNEL_SMEM : KMOS_B200_KERNEL_GENERIC;
+    b->kernel = b->smem_ok ? KMOS_B200_KERNEL_SMEM : (b->li_ok ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC);
     *out = b;
     return KMOS_B200_OK;
 }
@@ -500,10 +540,14 @@ extern "C" void kmos_b200_batch_destroy(kmos_b200_batch* b) {
 extern "C" int kmos_b200_batch_volume(const kmos_b200_batch* b) { return b->g.volume; }
 
 extern "C" int kmos_b200_select_kernel(kmos_b200_batch* b, int32_t kind) {
-    if (kind == KMOS_B200_KERNEL_AUTO) kind = b->smem_ok ? KMOS_B200_KERNEL_SMEM : KMOS_B200_KERNEL_GENERIC;
+    if (kind == KMOS_B200_KERNEL_AUTO)
+        kind = b->smem_ok ? KMOS_B200_KERNEL_SMEM : (b->li_ok ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC);
     if (kind == KMOS_B200_KERNEL_SMEM && !b->smem_ok)
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "shared-memory kernel unavailable: " + b->smem_reason);
-    if (kind != KMOS_B200_KERNEL_SMEM && kind != KMOS_B200_KERNEL_GENERIC) return set_err(KMOS_B200_ERR_ARG, "bad kernel kind");
+    if (kind == KMOS_B200_KERNEL_WARP_HBM && !b->li_ok)
+        return set_err(KMOS_B200_ERR_UNSUPPORTED, "warp-per-replica HBM kernel unavailable for this model/lattice");
+    if (kind != KMOS_B200_KERNEL_SMEM && kind != KMOS_B200_KERNEL_GENERIC && kind != KMOS_B200_KERNEL_WARP_HBM)
+        return set_err(KMOS_B200_ERR_ARG, "bad kernel kind");
     b->kernel = kind;
     return KMOS_B200_OK;
 }
@@ -515,6 +559,9 @@ extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[12]) {
         info[1] = b->wpc; info[2] = b->smem_bytes; info[3] = b->ctas_per_sm; info[4] = b->sm_count;
         info[5] = b->sp.rep_bytes; info[6] = (int64_t)b->sp.dev_words * 4; info[7] = (b->R + b->wpc - 1) / b->wpc;
         info[8] = b->sp.p1_global; info[9] = b->regs; info[10] = b->sp.split; info[11] = b->sp.img_bytes;
+    } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM) {
+        info[1] = b->li_wpc; info[2] = b->li_smem_bytes; info[4] = b->sm_count; info[5] = b->li.rep_bytes;
+        info[6] = (int64_t)b->li.dev_words * 4; info[7] = (b->R + b->li_wpc - 1) / b->li_wpc; info[8] = 1;
     } else {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, b->device) == cudaSuccess) info[4] = prop.multiProcessorCount;
@@ -686,6 +733,23 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     if (n == 0) return KMOS_B200_OK;
     if (b->kernel == KMOS_B200_KERNEL_GENERIC) return launch_generic(b, KB_MODE_STEPS, n, 0, -1);
     CU(cudaSetDevice(b->device));
+    if (b->kernel == KMOS_B200_KERNEL_WARP_HBM) {
+        int rc0 = ensure_canonical(b);
+        if (rc0) return rc0;
+        KbLatintParams li = b->li;
+        li.dev = b->d.dev;
+        li.lattice = b->lattice; li.lat_stride = b->lat_stride; li.nsites = b->nsites; li.p1 = b->p1; li.p2 = b->p2;
+        li.plane_elems = b->plane_bytes / (b->idx32 ? 4 : 2);
+        li.rates = b->rates; li.integ = b->integ; li.procstat = b->procstat; li.sc = b->sc; li.R = b->R; li.nsteps = n;
+        const int blocks = (b->R + b->li_wpc - 1) / b->li_wpc, threads = b->li_wpc * 32;
+        void (*fn)(const KbLatintParams);
+        if (b->model->h.n_proc > 32) fn = b->idx32 ? kb_latint_kernel<2, uint32_t> : kb_latint_kernel<2, uint16_t>;
+        else fn = b->idx32 ? kb_latint_kernel<1, uint32_t> : kb_latint_kernel<1, uint16_t>;
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->li_smem_bytes));
+        fn<<<blocks, threads, b->li_smem_bytes, b->stream>>>(li);
+        CU(cudaGetLastError());
+        return KMOS_B200_OK;
+    }
     int rc = ensure_compact(b);
     if (rc) return rc;
     KbSmemParams sp = smem_params(b);

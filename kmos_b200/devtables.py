@@ -245,8 +245,10 @@ def compile_device_tables(ir, asm=None):
     info = {"supported": False}
     nproc = len(ir["procs"])
     header = [DEV_VERSION, 0] + [0] * (HEADER_WORDS - 2)
+    if ir["backend"] == "lat_int":
+        return compile_latint_tables(ir)
     if ir["backend"] != "local_smart":
-        info["reason"] = "shared-memory tables are generated for local_smart only"
+        info["reason"] = "lane tables are generated for local_smart and lat_int only"
         return header, info
     try:
         from .tables import proc_anchor_types
@@ -410,4 +412,160 @@ def compile_device_tables(ir, asm=None):
                  "n_offsets": len(offsets_words), "n_classes": len(classes), "n_arenas": n_arenas,
                  "classes": classes, "spare": spare, "max_rounds": max_rounds, "max_ops": max_ops, "max_ncond": max_ncond,
                  "per_event": stats, "bytes": 4 * len(words), "proc_anchor": proc_anchor})
+    return [s32(w) for w in words], info
+
+
+# ======================================================================================================
+# lat_int: tables for the warp-per-replica kernel (kb_latint.cuh)
+# ======================================================================================================
+#
+# run_proc_<group>(cell) of the lat_int generator (kmos/io/__init__.py:1793-1983) has a fixed shape:
+#     del_proc(nli_g(cell + o), cell + o + (0,0,0,1))   for a sorted list of (g, o)
+#     replace_species(...)                               the group's actions
+#     add_proc(nli_g(cell + o), cell + o + (0,0,0,1))   the same list
+# and nli_<g>(cell) (io/__init__.py:1985-2057) is a decision tree over lattice species ending in a process
+# number or 0.  One lane evaluates one (g, o) pair; lanes that resolve to the same process run in lane
+# (= textual) order, everything else concurrently.
+#
+# Section layout (int32 words, offsets relative to the section start):
+#     [0] version=3 [1] supported [2] n_events [3] events_off [4] ops_off [5] n_ops [6] nodes_off
+#     [7] offsets_off [8] n_offsets [9] n_nodes [10] n_species [11] writes_off [12] n_writes
+#     [13] max_ops_per_phase [14..15] reserved
+#     events  4 words per process: dels_start, n_dels | n_adds<<16, adds_start, writes_start | n_writes<<16
+#     ops     1 word: root node | off_id<<16                      (off_id: cell the function is evaluated on)
+#     writes  1 word: off_id | n<<8 | (old+1)<<16 | (new+1)<<24   (species + 1: null_species = 0)
+#     nodes   (1 + n_species) words: off_id | n<<8 ; per species: 0x80000000 | process  or  child node index
+#     offsets 1 word: (dx&255) | (dy&255)<<8 | (dz&255)<<16
+LATINT_VERSION = 3
+
+
+def _tree_nodes(stmts, n_species, off_id, nodes, memo):
+    """Flatten the statement list of an nli function into decision-tree nodes; returns the reference of its
+    root: 0x80000000 | process for a leaf, else a node index."""
+    key = repr(stmts)
+    if key in memo:
+        return memo[key]
+    if not stmts:
+        return 0x80000000
+    st = stmts[0]
+    if st[0] == "return":
+        return 0x80000000 | int(st[1])
+    if st[0] != "select":
+        raise Unsupported("statement %r in nli function" % st[0])
+    rest = stmts[1:]
+    idx = len(nodes)
+    nodes.append(None)
+    children = []
+    for s in range(n_species):
+        body = None
+        default = None
+        for keyset, b in st[2]:
+            if keyset is None:
+                default = b
+            elif s in keyset and body is None:
+                body = b
+        chosen = body if body is not None else default
+        seq = (chosen if chosen is not None else []) + rest
+        children.append(_tree_nodes(seq, n_species, off_id, nodes, memo))
+    nodes[idx] = [off_id(st[1]) | (st[1][3] << 8)] + children
+    memo[key] = idx
+    return idx
+
+
+def compile_latint_tables(ir):
+    info = {"supported": False}
+    header = [LATINT_VERSION, 0] + [0] * (HEADER_WORDS - 2)
+    if ir["backend"] != "lat_int":
+        info["reason"] = "not a lat_int model"
+        return header, info
+    nproc = len(ir["procs"])
+    n_species = len(ir["species"])
+    try:
+        if nproc > 64:
+            raise Unsupported("more than 64 processes")
+        offsets = {}
+
+        def off_id(o):
+            key = (o[0], o[1], o[2])
+            for d in key:
+                if not -128 <= d <= 127:
+                    raise Unsupported("offset out of byte range")
+            if key not in offsets:
+                if len(offsets) == 255:
+                    raise Unsupported("too many distinct offsets")
+                offsets[key] = len(offsets)
+            return offsets[key]
+
+        off_id([0, 0, 0])
+        nodes, roots = [], {}
+        for name, stmts in sorted(ir["nli"].items()):
+            root = _tree_nodes(stmts, n_species, off_id, nodes, {})
+            if root & 0x80000000:  # a constant function: wrap it into a one-node tree on the cell itself
+                idx = len(nodes)
+                nodes.append([off_id([0, 0, 0]) | (1 << 8)] + [root] * n_species)
+                root = idx
+            roots[name] = root
+        if len(nodes) >= 1 << 16:
+            raise Unsupported("decision trees too large")
+        ops_words, writes_words, events_words = [], [], []
+        cache = {}
+        max_phase = 0
+        for p in range(nproc):
+            calls = ir["run_proc"][p]
+            if len(calls) != 1 or calls[0][2] != [0, 0, 0, -1]:
+                raise Unsupported("run_proc_nr of process %d is not a single cell routine" % (p + 1))
+            rname = calls[0][1]
+            if rname not in cache:
+                dels, adds, writes = [], [], []
+                phase = 0
+                for st in ir["routines"][rname]:
+                    if st[0] in ("del", "add"):
+                        if not isinstance(st[1], list) or st[1][0] != "nli":
+                            raise Unsupported("lat_int op without nli function")
+                        celloff, siteoff = st[1][2], st[2]
+                        if celloff[3] != 0 or siteoff[:3] != celloff[:3] or siteoff[3] != 1:
+                            raise Unsupported("lat_int op not registered on site 1 of the evaluated cell")
+                        word = roots[st[1][1]] | (off_id(celloff) << 16)
+                        if st[0] == "del":
+                            if phase != 0:
+                                raise Unsupported("del after lattice update")
+                            dels.append(word)
+                        else:
+                            phase = 2
+                            adds.append(word)
+                    elif st[0] == "replace":
+                        if phase == 2:
+                            raise Unsupported("lattice update after add")
+                        phase = 1
+                        writes.append(off_id(st[1]) | (st[1][3] << 8) | ((st[2] + 1) << 16) | ((st[3] + 1) << 24))
+                    else:
+                        raise Unsupported("statement %r in lat_int run_proc" % st[0])
+                ev = [len(ops_words), len(dels) | (len(adds) << 16), len(ops_words) + len(dels),
+                      len(writes_words) | (len(writes) << 16)]
+                ops_words += dels + adds
+                writes_words += writes
+                max_phase = max(max_phase, len(dels), len(adds))
+                cache[rname] = ev
+            events_words += cache[rname]
+        offsets_words = [0] * len(offsets)
+        for (dx, dy, dz), i in offsets.items():
+            offsets_words[i] = (dx & 255) | ((dy & 255) << 8) | ((dz & 255) << 16)
+        nodes_words = [w for nd in nodes for w in nd]
+    except Unsupported as e:
+        info["reason"] = str(e)
+        return header, info
+
+    def s32(w):
+        return w - (1 << 32) if w >= (1 << 31) else w
+
+    events_off = HEADER_WORDS
+    ops_off = events_off + len(events_words)
+    writes_off = ops_off + len(ops_words)
+    nodes_off = writes_off + len(writes_words)
+    offsets_off = nodes_off + len(nodes_words)
+    header = [LATINT_VERSION, 1, nproc, events_off, ops_off, len(ops_words), nodes_off, offsets_off,
+              len(offsets_words), len(nodes), n_species, writes_off, len(writes_words), max_phase, 0, 0]
+    words = header + events_words + ops_words + writes_words + nodes_words + offsets_words
+    info.update({"supported": True, "n_ops": len(ops_words), "n_nodes": len(nodes), "n_offsets": len(offsets_words),
+                 "max_ops_per_phase": max_phase, "bytes": 4 * len(words)})
     return [s32(w) for w in words], info

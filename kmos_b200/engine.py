@@ -83,7 +83,8 @@ class Batch(object):
                 "state_bytes_per_replica", "table_bytes", "grid", "lists_in_l2", "registers", "split_lists",
                 "image_bytes_per_replica")
         d = dict(zip(keys, (int(x) for x in info)))
-        d["kernel_name"] = {capi.KERNEL_GENERIC: "generic", capi.KERNEL_SMEM: "smem"}[d["kernel"]]
+        d["kernel_name"] = {capi.KERNEL_GENERIC: "generic", capi.KERNEL_SMEM: "smem",
+                            capi.KERNEL_WARP_HBM: "warp_hbm"}[d["kernel"]]
         return d
 
     def set_seeds(self, seeds, replica_ids=None):

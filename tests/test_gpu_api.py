@@ -49,15 +49,19 @@ def test_kernel_selection_and_fallback_reasons():
     ir, blob, info = load_model("pairwise_lat_int")
     m = engine.Model(ir=ir, blob=blob, info=info)
     b = engine.Batch(m, 2, [8, 8], rates=np.ones((2, 19)))
-    assert b.kernel_info()["kernel_name"] == "generic"
+    assert b.kernel_info()["kernel_name"] == "warp_hbm"
     with pytest.raises(capi.KmosB200Error, match="shared-memory kernel unavailable"):
         b.select_kernel(capi.KERNEL_SMEM)
+    b.select_kernel(capi.KERNEL_GENERIC)
+    assert b.kernel_info()["kernel_name"] == "generic"
     b.close()
     # a lattice smaller than twice the interaction range cannot use the compact class entries
     ir, blob, info = load_model("zgb_local_smart")
     m = engine.Model(ir=ir, blob=blob, info=info)
     b = engine.Batch(m, 2, [2, 2], rates=np.ones((2, 10)))
     assert b.kernel_info()["kernel_name"] == "generic"
+    with pytest.raises(capi.KmosB200Error, match="warp-per-replica HBM kernel unavailable"):
+        b.select_kernel(capi.KERNEL_WARP_HBM)
     b.do_steps(50)
     assert np.all(b.kmc_step == 50)
     b.close()

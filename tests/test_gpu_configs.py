@@ -59,7 +59,7 @@ def test_config3_pairwise_lat_int_128x128_2048_replicas():
     rates = workloads.rates_for("pairwise", ir, R) * (1.0 + 0.001 * (np.arange(R) % 7))[:, None]
     seeds = np.arange(R, dtype=np.uint64) + np.uint64(99)
     b = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, [128, 128], seeds=seeds, rates=rates)
-    assert b.kernel_info()["kernel_name"] == "generic"
+    assert b.kernel_info()["kernel_name"] == "warp_hbm"
     b.do_steps(n)
     _check_sample(b, blob, [128, 128], seeds, rates, None, n, [0, 2047], avail=True)
 

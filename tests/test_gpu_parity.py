@@ -48,19 +48,43 @@ def test_local_smart_parity(name, size, R, chunks, kernel):
     batch.close()
 
 
-GENERIC_CASES = [
+LATINT_CASES = [
     ("ab_lat_int", [10, 12], 6, [1500, 1500]),
-    ("ab_otf", [10, 12], 6, [1500, 1500]),
+    ("mini_101_lat_int", [7, 5], 5, [700, 700]),
     ("zgb_lat_int", [12, 12], 5, [2000, 2000]),
     ("ruo2_lat_int", [8, 8], 5, [1500, 1500]),
     ("pairwise_lat_int", [16, 16], 8, [2000, 2000]),
+    ("pairwise_lat_int", [5, 3], 3, [1000]),
+]
+
+
+@pytest.mark.parametrize("name,size,R,chunks", LATINT_CASES)
+@pytest.mark.parametrize("kernel", ["warp_hbm", "generic"])
+def test_lat_int_parity(name, size, R, chunks, kernel):
+    engine = _engine()
+    ir, blob, info = load_model(name)
+    rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + 1)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    kind = capi.KERNEL_WARP_HBM if kernel == "warp_hbm" else capi.KERNEL_GENERIC
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=kind)
+    assert batch.kernel_info()["kernel_name"] == kernel
+    gen = run_oracles(blob, size, rates, lut, seeds, chunks)
+    compare_batch(batch, next(gen), avail_replicas=(0,))
+    for n, oracles in zip(chunks, gen):
+        batch.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(0, R - 1))
+    batch.close()
+
+
+OTF_CASES = [
+    ("ab_otf", [10, 12], 6, [1500, 1500]),
     ("pairwise_otf_otf", [16, 16], 8, [2000, 2000]),
     ("mini_101_otf", [6, 6], 4, [500, 500]),
 ]
 
 
-@pytest.mark.parametrize("name,size,R,chunks", GENERIC_CASES)
-def test_lat_int_and_otf_parity(name, size, R, chunks):
+@pytest.mark.parametrize("name,size,R,chunks", OTF_CASES)
+def test_otf_parity(name, size, R, chunks):
     engine = _engine()
     ir, blob, info = load_model(name)
     rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + 1)

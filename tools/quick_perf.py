@@ -42,7 +42,9 @@ if __name__ == "__main__":
                 ("zgb_local_smart", [64, 64], 4096, 1000, capi.KERNEL_SMEM),
                 ("ruo2_local_smart", [20, 20], 16384, 2000, capi.KERNEL_SMEM),
                 ("ruo2_local_smart", [20, 20], 16384, 200, capi.KERNEL_GENERIC),
+                ("pairwise_lat_int", [128, 128], 2048, 2000, capi.KERNEL_WARP_HBM),
                 ("pairwise_lat_int", [128, 128], 2048, 200, capi.KERNEL_GENERIC),
+                ("ruo2_lat_int", [20, 20], 16384, 1000, capi.KERNEL_WARP_HBM),
                 ("pairwise_otf_otf", [64, 64], 512, 100, capi.KERNEL_GENERIC)],
     }[which]
     for c in cases:
