@@ -59,6 +59,12 @@ struct KbSmemParams {
     KbScalars* sc;
     int R;
     long long nsteps;
+    // persistent scheduling: work item i = (epoch i / R, replica i % R); an epoch is `chunk` steps.  Warps
+    // fetch items from `work_counter`; `done[r]` counts the finished epochs of replica r in this launch.
+    int* work_counter;
+    int* done;
+    int n_items;
+    long long chunk;
     // shared-memory layout (bytes)
     int tab_bytes, rep_bytes;
     int off_hi, off_p2;                                   // offsets inside the compact image
@@ -114,6 +120,15 @@ __device__ __forceinline__ void kb_bulk_commit_wait() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void kb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void kb_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int kb_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void kb_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ int kb_s8(uint32_t w, int shift) { return (int)(int8_t)((w >> shift) & 255u); }
 
@@ -267,7 +282,7 @@ struct KbCellCtx {
 //   w1 = class base (cls * ncells) | first slot of the list (arena*cap, or arena*cap + cap-1 if it grows down) << 16
 //   then ncond probe words off_id | n<<5 | mask<<8
 template <int PPL, int NCOND, bool SPLIT, bool P1G, bool NBT>
-__global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemParams prm) {
+__global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemParams prm) {
     extern __shared__ __align__(128) unsigned char kb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
@@ -294,15 +309,41 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
         }
         __syncthreads();
     }
-    const int rep = blockIdx.x * wpc + warp;
-    if (rep >= prm.R) return;  // no block-wide barrier below this line
-
+    // no block-wide barrier below this line: every warp is an independent worker
     unsigned char* base = kb_smem + prm.tab_bytes + prm.nbt_bytes + (size_t)warp * prm.rep_bytes;
     uint16_t* p2 = reinterpret_cast<uint16_t*>(base + prm.sm_p2);
     uint8_t* lat = base + prm.sm_lat;
     int32_t* nS = reinterpret_cast<int32_t*>(base + prm.sm_ns);
     double* prodS = reinterpret_cast<double*>(base + prm.sm_prod);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(base + prm.sm_mbar);
+    if (prm.use_bulk) {
+        if (lane == 0) {
+            kb_mbar_init(mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    uint32_t mbar_phase = 0;
+    (void)wpc;
+
+  for (;;) {  // ---- persistent worker loop: one (epoch, replica) item per iteration -------------------------
+    int item = 0;
+    if (lane == 0) item = atomicAdd(prm.work_counter, 1);
+    item = __shfl_sync(KB_FULL, item, 0);
+    if (item >= prm.n_items) break;
+    const int epoch = item / prm.R;
+    const int rep = item - epoch * prm.R;
+    long long my_steps = prm.chunk;
+    if ((long long)epoch * prm.chunk + my_steps > prm.nsteps) my_steps = prm.nsteps - (long long)epoch * prm.chunk;
+    if (epoch > 0) {
+        // the previous epoch of this replica was handed out earlier to a resident warp: wait for its write-back
+        if (lane == 0) {
+            while (kb_ld_acquire(prm.done + rep) < epoch) __nanosleep(128);
+        }
+        __syncwarp();
+        __threadfence();
+        kb_fence_proxy_async_all();
+    }
 
     const int P = prm.n_proc, C = prm.ncells, cap = prm.cap, spuck = prm.spuck;
     unsigned char* g_img = reinterpret_cast<unsigned char*>(prm.image) + (size_t)rep * prm.img_bytes;
@@ -318,16 +359,12 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
     // ---- stage the replica into shared memory (the image is laid out exactly like p1|p2 here) ---------
     if (prm.use_bulk) {
         if (lane == 0) {
-            kb_mbar_init(mbar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-        if (lane == 0) {
             kb_mbar_expect_tx(mbar, (uint32_t)(prm.stage_bytes + prm.lat_stride));
             kb_bulk_g2s(base, g_stage, (uint32_t)prm.stage_bytes, mbar);
             kb_bulk_g2s(lat, g_lat, (uint32_t)prm.lat_stride, mbar);
         }
-        kb_mbar_wait(mbar, 0);
+        kb_mbar_wait(mbar, mbar_phase);
+        mbar_phase ^= 1u;
     } else {
         const uint4* s1 = reinterpret_cast<const uint4*>(g_stage);
         uint4* d1 = reinterpret_cast<uint4*>(base);
@@ -366,7 +403,7 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
 
     double rng_a = 0.0, rng_b = 0.0;  // even lanes: (-log(ran_time), ran_proc); odd lanes: (ran_site, -)
 
-    for (long long it = 0; it < prm.nsteps && status == KB_OK; ++it) {
+    for (long long it = 0; it < my_steps && status == KB_OK; ++it) {
         const int sub = (int)(it & (KB_RNG_BATCH - 1));
         if (sub == 0) {
             // 16 steps of uniforms at once: lane l serves step kmc_step + l/2, Philox slot l&1
@@ -538,6 +575,7 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
             kb_bulk_s2g(g_stage, base, (uint32_t)prm.stage_bytes);
             kb_bulk_s2g(g_lat, lat, (uint32_t)prm.lat_stride);
             kb_bulk_commit_wait();
+            kb_fence_proxy_async_all();
         }
     } else {
         uint4* s1 = reinterpret_cast<uint4*>(g_stage);
@@ -564,4 +602,10 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
         if (bad) { out.err[0] = err0; out.err[1] = err1; out.err[2] = err2; out.err[3] = err3; out.err[4] = err4; }
         prm.sc[rep] = out;
     }
+    // publish: everything this warp wrote for the replica is visible before the epoch counter moves
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) kb_st_release(prm.done + rep, epoch + 1);
+    __syncwarp();  // the shared-memory block is reused by the next item
+  }
 }

@@ -76,6 +76,7 @@ struct kmos_b200_batch {
     kb_smem_fn fn;
     std::vector<int32_t> spec;  // lane tables specialised for this geometry (host copy)
     int32_t* d_spec;
+    int* d_sched;  // [0] work counter, [1..R] finished epochs per replica (persistent scheduling)
     bool smem_ok;
     std::string smem_reason;
     bool li_ok;  // warp-per-replica lat_int kernel available
@@ -416,9 +417,9 @@ static void plan_smem(kmos_b200_batch* b) {
             if (n < 1) continue;
             // score: resident replicas per SM x how full the last wave of this batch is; the lists-in-L2
             // placement pays ~1.5x more latency per step, so it must bring that many more replicas
-            const double waves = (double)b->R / ((double)prop.multiProcessorCount * n * w);
-            const double eff = waves / ceil(waves);
-            const double score = n * w * eff / (p1g ? 1.5 : 1.0);
+            // score: resident replicas per SM (work is handed out dynamically in epochs, so the fill of the
+            // last wave does not matter); the lists-in-L2 placement pays ~1.5x more latency per step
+            const double score = n * w / (p1g ? 1.5 : 1.0);
             if (score > best_score * 1.0001 || (score > best_score * 0.9999 && n * w < best_total)) {
                 best_score = score; best_total = n * w; best = c;
                 b->wpc = w; b->ctas_per_sm = n; b->smem_bytes = c.tab_bytes + c.nbt_bytes + w * c.rep_bytes;
@@ -515,7 +516,9 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     b->image = nullptr;
     b->compact_valid = false;
     b->d_spec = nullptr;
+    b->d_sched = nullptr;
     if (b->smem_ok) {
+        CU(cudaMalloc(&b->d_sched, ((size_t)R + 1) * sizeof(int)));
         CU(cudaMalloc(&b->image, (size_t)R * b->sp.img_bytes));
         CU(cudaMalloc(&b->d_spec, b->spec.size() * 4));
         CU(cudaMemcpy(b->d_spec, b->spec.data(), b->spec.size() * 4, cudaMemcpyHostToDevice));
@@ -531,7 +534,7 @@ extern "C" void kmos_b200_batch_destroy(kmos_b200_batch* b) {
     cudaStreamSynchronize(b->stream);
     cudaFree(b->d_blob); cudaFree(b->lattice); cudaFree(b->p1); cudaFree(b->p2); cudaFree(b->nsites);
     cudaFree(b->rates); cudaFree(b->integ); cudaFree(b->accum); cudaFree(b->procstat); cudaFree(b->sc);
-    cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->occ); cudaFree(b->group_of); cudaFree(b->image); cudaFree(b->d_spec);
+    cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->occ); cudaFree(b->group_of); cudaFree(b->image); cudaFree(b->d_spec); cudaFree(b->d_sched);
     cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
     cudaStreamDestroy(b->own_stream);
     delete b;
@@ -557,7 +560,9 @@ extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[12]) {
     info[0] = b->kernel;
     if (b->kernel == KMOS_B200_KERNEL_SMEM) {
         info[1] = b->wpc; info[2] = b->smem_bytes; info[3] = b->ctas_per_sm; info[4] = b->sm_count;
-        info[5] = b->sp.rep_bytes; info[6] = (int64_t)b->sp.dev_words * 4; info[7] = (b->R + b->wpc - 1) / b->wpc;
+        info[5] = b->sp.rep_bytes; info[6] = (int64_t)b->sp.dev_words * 4;
+        info[7] = (b->R + b->wpc - 1) / b->wpc;
+        if (info[7] > (int64_t)b->sm_count * b->ctas_per_sm) info[7] = (int64_t)b->sm_count * b->ctas_per_sm;
         info[8] = b->sp.p1_global; info[9] = b->regs; info[10] = b->sp.split; info[11] = b->sp.img_bytes;
     } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM) {
         info[1] = b->li_wpc; info[2] = b->li_smem_bytes; info[4] = b->sm_count; info[5] = b->li.rep_bytes;
@@ -755,7 +760,29 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     KbSmemParams sp = smem_params(b);
     sp.nsteps = n;
     const int threads = b->wpc * 32;
-    const int blocks = (b->R + b->wpc - 1) / b->wpc;
+    // persistent CTAs: as many as stay resident; warps fetch (epoch, replica) items dynamically.  Splitting the
+    // n steps into epochs keeps the tail short when the replicas do not divide evenly over the warp slots.
+    int blocks = (b->R + b->wpc - 1) / b->wpc;
+    const int resident = b->sm_count * b->ctas_per_sm;
+    if (blocks > resident) blocks = resident;
+    const long long slots = (long long)blocks * b->wpc;
+    long long epochs = 1;
+    if (b->R > slots) {
+        epochs = (24 * slots + b->R - 1) / b->R;          // ~24 items per warp slot
+        const long long max_epochs = n / 256 > 0 ? n / 256 : 1;  // at least 256 steps per item
+        if (epochs > max_epochs) epochs = max_epochs;
+        if (epochs > 64) epochs = 64;
+        if (epochs < 1) epochs = 1;
+    }
+    const char* ep_env = getenv("KMOS_B200_EPOCHS");
+    if (ep_env && atoi(ep_env) > 0) epochs = atoi(ep_env);
+    sp.chunk = (n + epochs - 1) / epochs;
+    epochs = (n + sp.chunk - 1) / sp.chunk;
+    if (epochs * (long long)b->R > 0x7fffffffLL) return set_err(KMOS_B200_ERR_ARG, "do_kmc_steps: too many work items");
+    sp.n_items = (int)(epochs * b->R);
+    sp.work_counter = b->d_sched;
+    sp.done = b->d_sched + 1;
+    CU(cudaMemsetAsync(b->d_sched, 0, ((size_t)b->R + 1) * sizeof(int), b->stream));
     CU(cudaFuncSetAttribute(b->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
     b->fn<<<blocks, threads, b->smem_bytes, b->stream>>>(sp);
     CU(cudaGetLastError());
