@@ -75,3 +75,43 @@ def test_config4_pairwise_otf_256x256():
     assert b.kernel_info()["kernel_name"] == "generic"
     b.do_steps(n)
     _check_sample(b, blob, [256, 256], seeds, rates, lut, n, [0, 7], avail=True)
+
+
+def test_production_stream_statistics_within_3_sigma():
+    """north_star: production-stream runs must agree statistically with the reference.  GPU ensemble (one set
+    of Philox keys) vs CPU-oracle ensemble (a disjoint set of keys) of the ZGB model at y_CO = 0.45: the mean
+    coverages and the CO2 turn-over frequency agree within 3 standard errors."""
+    from kmos_b200 import engine, rates as rates_mod
+    from oracle import oracle
+    ir, blob, info = load_model("zgb_local_smart")
+    size, warm, n = [16, 16], 20000, 20000
+    r = np.asarray(rates_mod.model_rates(ir, {"yCO": 0.45}))
+    ox = [i for i, p in enumerate(ir["procs"]) if p.lower().startswith("co_oxidation")]
+
+    def observables(occ, ps0, ps1, t0, t1):
+        tof = (ps1 - ps0)[:, ox].sum(axis=1) / (t1 - t0) / (size[0] * size[1])
+        return np.column_stack([occ.reshape(len(occ), -1), tof])
+
+    R = 96
+    seeds = np.arange(R, dtype=np.uint64) + np.uint64(1000)
+    b = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=np.tile(r, (R, 1)))
+    b.do_steps(warm)
+    ps0, t0 = b.procstat, b.kmc_time
+    b.do_steps(n)
+    gpu = observables(b.occupation, ps0, b.procstat, t0, b.kmc_time)
+
+    Rc = 48
+    cpu_rows = []
+    for k in range(Rc):
+        o = oracle.Oracle(blob, size, seed=500000 + k, replica=k, rates=r)
+        o.do_steps(warm)
+        p0, tt0 = o.procstat.copy(), o.kmc_time
+        o.do_steps(n)
+        cpu_rows.append(observables(o.occupation[None], p0[None], o.procstat[None], np.array([tt0]),
+                                    np.array([o.kmc_time]))[0])
+    cpu = np.asarray(cpu_rows)
+    diff = gpu.mean(axis=0) - cpu.mean(axis=0)
+    sigma = np.sqrt(gpu.var(axis=0, ddof=1) / R + cpu.var(axis=0, ddof=1) / Rc)
+    ok = (np.abs(diff) <= 3 * sigma) | (sigma == 0)
+    assert ok.all(), (diff, sigma)
+    assert gpu[:, -1].mean() > 0  # the reactive window: CO2 is produced
