@@ -31,7 +31,8 @@
 #define KB20_MAGIC 0x4B423230
 #define KB20_VERSION 4
 
-enum { KB_SEC_ROUTINES = 1, KB_SEC_CODE, KB_SEC_RUNPROC, KB_SEC_INIT, KB_SEC_GR, KB_SEC_PROCSITE, KB_SEC_DEVICE };
+enum { KB_SEC_ROUTINES = 1, KB_SEC_CODE, KB_SEC_RUNPROC, KB_SEC_INIT, KB_SEC_GR, KB_SEC_PROCSITE, KB_SEC_DEVICE,
+       KB_SEC_DEVICE_HBM };
 enum {
     KB_OP_REPLACE = 1, KB_OP_IF_CAN, KB_OP_DEL, KB_OP_ADD, KB_OP_DEL_NLI, KB_OP_ADD_NLI, KB_OP_ADD_RATE,
     KB_OP_UPD_RATE, KB_OP_SELECT, KB_OP_CASE, KB_OP_DEL_ALL, KB_OP_CALL, KB_OP_RETURN, KB_OP_INC, KB_OP_JUMP
@@ -62,8 +63,8 @@ struct KbModelView {
     const int32_t* blob;
     int backend, n_species, n_proc, spuck, dim, default_species, n_layers, default_layer, n_routines, n_gr,
         lut_total;
-    const int32_t *routines, *code, *runproc, *init, *gr, *procsite, *dev;
-    int dev_len;
+    const int32_t *routines, *code, *runproc, *init, *gr, *procsite, *dev, *dev_hbm;
+    int dev_len, dev_hbm_len;
 };
 
 struct KbGeom {
@@ -177,6 +178,8 @@ static inline bool kb_model_view(const int32_t* hblob, int64_t n_words, const in
     KB_SEC(procsite, KB_SEC_PROCSITE)
     KB_SEC(dev, KB_SEC_DEVICE)
     m->dev_len = len;
+    KB_SEC(dev_hbm, KB_SEC_DEVICE_HBM)
+    m->dev_hbm_len = len;
 #undef KB_SEC
     return m->routines && m->code && m->runproc && m->init && m->procsite;
 }

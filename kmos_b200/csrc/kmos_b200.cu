@@ -81,7 +81,7 @@ struct kmos_b200_batch {
     std::string smem_reason;
     bool li_ok;  // warp-per-replica lat_int kernel available
     KbLatintParams li;
-    int li_wpc, li_smem_bytes;
+    int li_wpc, li_smem_bytes, li_mode;  // li_mode 0: lat_int decision trees, 1: local_smart flattened ops
 };
 
 extern "C" const char* kmos_b200_last_error(void) { return g_err.c_str(); }
@@ -310,8 +310,15 @@ static bool specialise_tables(const int32_t* d, int ncells, int cap, std::vector
 static void plan_latint(kmos_b200_batch* b) {
     const kmos_b200_model* m = b->model;
     b->li_ok = false;
-    const int32_t* d = m->h.dev;
-    if (m->h.backend != KB_BACKEND_LAT_INT || !d || m->h.dev_len < 16 || d[0] != 3 || d[1] != 1) return;
+    const int32_t* d = nullptr;
+    int dlen = 0;
+    if (m->h.backend == KB_BACKEND_LAT_INT && m->h.dev && m->h.dev_len >= 16 && m->h.dev[0] == 3 && m->h.dev[1] == 1) {
+        d = m->h.dev; dlen = m->h.dev_len; b->li_mode = 0;
+    } else if (m->h.backend == KB_BACKEND_LOCAL_SMART && m->h.dev_hbm && m->h.dev_hbm_len >= 16 &&
+               m->h.dev_hbm[0] == 4 && m->h.dev_hbm[1] == 1) {
+        d = m->h.dev_hbm; dlen = m->h.dev_hbm_len; b->li_mode = 1;
+    }
+    if (!d) return;
     if (m->h.n_proc > 64) return;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, b->device) != cudaSuccess) return;
@@ -328,7 +335,7 @@ static void plan_latint(kmos_b200_batch* b) {
     li.magic_x = (uint32_t)((0x100000000ull / (uint64_t)Lx) + 1);
     li.magic_xy = (uint32_t)((0x100000000ull / (uint64_t)LxLy) + 1);
     if (!magic_ok(li.magic_x, Lx, b->g.ncells) || !magic_ok(li.magic_xy, LxLy, b->g.ncells)) return;
-    li.dev_words = m->h.dev_len;
+    li.dev_words = dlen;
     li.tab_bytes = (int)align_up((size_t)li.dev_words * 4, 128);
     li.rep_bytes = 1280;  // nr_of_sites (256 B) + two zero-prefixed product buffers (1 KB)
     b->li_wpc = 8;
@@ -742,14 +749,20 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         int rc0 = ensure_canonical(b);
         if (rc0) return rc0;
         KbLatintParams li = b->li;
-        li.dev = b->d.dev;
+        li.dev = b->li_mode ? b->d.dev_hbm : b->d.dev;
         li.lattice = b->lattice; li.lat_stride = b->lat_stride; li.nsites = b->nsites; li.p1 = b->p1; li.p2 = b->p2;
         li.plane_elems = b->plane_bytes / (b->idx32 ? 4 : 2);
         li.rates = b->rates; li.integ = b->integ; li.procstat = b->procstat; li.sc = b->sc; li.R = b->R; li.nsteps = n;
         const int blocks = (b->R + b->li_wpc - 1) / b->li_wpc, threads = b->li_wpc * 32;
         void (*fn)(const KbLatintParams);
-        if (b->model->h.n_proc > 32) fn = b->idx32 ? kb_latint_kernel<2, uint32_t> : kb_latint_kernel<2, uint16_t>;
-        else fn = b->idx32 ? kb_latint_kernel<1, uint32_t> : kb_latint_kernel<1, uint16_t>;
+        const bool p2l = b->model->h.n_proc > 32;
+        if (b->li_mode == 0) {
+            if (p2l) fn = b->idx32 ? kb_latint_kernel<2, uint32_t, 0> : kb_latint_kernel<2, uint16_t, 0>;
+            else fn = b->idx32 ? kb_latint_kernel<1, uint32_t, 0> : kb_latint_kernel<1, uint16_t, 0>;
+        } else {
+            if (p2l) fn = b->idx32 ? kb_latint_kernel<2, uint32_t, 1> : kb_latint_kernel<2, uint16_t, 1>;
+            else fn = b->idx32 ? kb_latint_kernel<1, uint32_t, 1> : kb_latint_kernel<1, uint16_t, 1>;
+        }
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->li_smem_bytes));
         fn<<<blocks, threads, b->li_smem_bytes, b->stream>>>(li);
         CU(cudaGetLastError());

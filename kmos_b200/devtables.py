@@ -569,3 +569,94 @@ def compile_latint_tables(ir):
     info.update({"supported": True, "n_ops": len(ops_words), "n_nodes": len(nodes), "n_offsets": len(offsets_words),
                  "max_ops_per_phase": max_phase, "bytes": 4 * len(words)})
     return [s32(w) for w in words], info
+
+
+# ======================================================================================================
+# local_smart on lattices that do not fit shared memory: tables for the warp-per-replica HBM kernel
+# ======================================================================================================
+#
+# Same flattened events as the shared-memory tables (flatten_event) but kept in textual order and executed on
+# the canonical per-process planes: the only ordering that matters is between ops of the same process, which
+# the kernel resolves with a warp match, like for lat_int.
+#
+# Section layout (int32 words):
+#     [0] version=4 [1] supported [2] n_events [3] events_off [4] ops_off [5] n_ops [6] op_stride
+#     [7] offsets_off [8] n_offsets [9..10] 0 [11] writes_off [12] n_writes [13] max_ops_per_event
+#     events  4 words per process: ops_start (op index), n_ops, writes_start | n_writes<<16, base site type
+#     ops     op_stride words: kind | ncond<<1 | off_id<<4 | q<<12 ; then ncond words off_id | n<<8 | mask<<16
+#     writes  off_id | n<<8 | (old+1)<<16 | (new+1)<<24
+#     offsets (dx&255) | (dy&255)<<8 | (dz&255)<<16
+HBM_VERSION = 4
+
+
+def compile_hbm_tables(ir):
+    info = {"supported": False}
+    header = [HBM_VERSION, 0] + [0] * (HEADER_WORDS - 2)
+    if ir["backend"] != "local_smart":
+        info["reason"] = "not a local_smart model"
+        return header, info
+    nproc = len(ir["procs"])
+    try:
+        from .tables import proc_anchor_types
+        proc_anchor = proc_anchor_types(ir)
+        if any(a == 0 for a in proc_anchor):
+            raise Unsupported("a process is registered on several site types")
+        if nproc > 64:
+            raise Unsupported("more than 64 processes")
+        if len(ir["species"]) > 16:
+            raise Unsupported("more than 16 species")
+        offsets = {}
+
+        def off_id(o):
+            key = (o[0], o[1], o[2])
+            for d in key:
+                if not -128 <= d <= 127:
+                    raise Unsupported("offset out of byte range")
+            if key not in offsets:
+                if len(offsets) == 255:
+                    raise Unsupported("too many distinct offsets")
+                offsets[key] = len(offsets)
+            return offsets[key]
+
+        off_id([0, 0, 0])
+        flat = [flatten_event(ir, p) for p in range(nproc)]
+        max_ncond = max([len(op[3]) for _b, _w, ops in flat for op in ops] + [0])
+        stride = 1 + max_ncond
+        ops_words, writes_words, events_words = [], [], []
+        max_ops = 0
+        for p, (base_n, writes, ops) in enumerate(flat):
+            if base_n != proc_anchor[p]:
+                raise Unsupported("process %d is selected on another site type than it is registered on" % (p + 1))
+            ev = [len(ops_words) // stride, len(ops), len(writes_words) | (len(writes) << 16), base_n]
+            for kind, q, aoff, cs, _g in ops:
+                if aoff[3] != proc_anchor[q - 1]:
+                    raise Unsupported("anchor site type mismatch")
+                words = [kind | (len(cs) << 1) | (off_id(aoff) << 4) | (q << 12)]
+                for site, mask in cs:
+                    words.append(off_id(site) | (site[3] << 8) | (mask << 16))
+                words += [0] * (stride - len(words))
+                ops_words += words
+            for off, old, new in writes:
+                writes_words.append(off_id(off) | (off[3] << 8) | ((old + 1) << 16) | ((new + 1) << 24))
+            events_words += ev
+            max_ops = max(max_ops, len(ops))
+        offsets_words = [0] * len(offsets)
+        for (dx, dy, dz), i in offsets.items():
+            offsets_words[i] = (dx & 255) | ((dy & 255) << 8) | ((dz & 255) << 16)
+    except Unsupported as e:
+        info["reason"] = str(e)
+        return header, info
+
+    def s32(w):
+        return w - (1 << 32) if w >= (1 << 31) else w
+
+    events_off = HEADER_WORDS
+    ops_off = events_off + len(events_words)
+    writes_off = ops_off + len(ops_words)
+    offsets_off = writes_off + len(writes_words)
+    header = [HBM_VERSION, 1, nproc, events_off, ops_off, len(ops_words) // stride, stride, offsets_off,
+              len(offsets_words), 0, 0, writes_off, len(writes_words), max_ops, 0, 0]
+    words = header + events_words + ops_words + writes_words + offsets_words
+    info.update({"supported": True, "n_ops": len(ops_words) // stride, "op_stride": stride,
+                 "max_ops_per_event": max_ops, "bytes": 4 * len(words)})
+    return [s32(w) for w in words], info

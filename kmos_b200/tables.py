@@ -18,6 +18,7 @@ Sections
     SEC_GR         otf: n_gr x (routine, proc, nvars, lut_offset, radix[MAX_VARS])
     SEC_PROCSITE   n_proc x site type (1-based) the process is registered on (0: several -> unsupported)
     SEC_DEVICE     compiled per-event lane tables for the CUDA engine (kmos_b200.devtables)
+    SEC_DEVICE_HBM local_smart only: the same events in textual order for the HBM-resident warp kernel
 
 Coordinates are 4-vectors [dx,dy,dz,dn] added to the routine's base coordinate, exactly like the
 `site + (/dx,dy,dz,dn/)` expressions of the generated code (lattice.mpy:343-491).
@@ -29,7 +30,7 @@ VERSION = 4
 
 BACKENDS = {"local_smart": 0, "lat_int": 1, "otf": 2}
 
-SEC_ROUTINES, SEC_CODE, SEC_RUNPROC, SEC_INIT, SEC_GR, SEC_PROCSITE, SEC_DEVICE = range(1, 8)
+SEC_ROUTINES, SEC_CODE, SEC_RUNPROC, SEC_INIT, SEC_GR, SEC_PROCSITE, SEC_DEVICE, SEC_DEVICE_HBM = range(1, 9)
 
 (OP_REPLACE, OP_IF_CAN, OP_DEL, OP_ADD, OP_DEL_NLI, OP_ADD_NLI, OP_ADD_RATE, OP_UPD_RATE, OP_SELECT,
  OP_CASE, OP_DEL_ALL, OP_CALL, OP_RETURN, OP_INC, OP_JUMP) = range(1, 16)
@@ -266,6 +267,10 @@ def build_blob(ir, with_device=True):
         dev_words, dev_info = devtables.compile_device_tables(ir, asm)
         sections.append((SEC_DEVICE, dev_words))
         info["device"] = dev_info
+        if ir["backend"] == "local_smart":
+            hbm_words, hbm_info = devtables.compile_hbm_tables(ir)
+            sections.append((SEC_DEVICE_HBM, hbm_words))
+            info["device_hbm"] = hbm_info
 
     header = [MAGIC, VERSION, BACKENDS[ir["backend"]], len(ir["species"]), nproc, ir["spuck"],
               ir["model_dimension"], ir["default_species"], nlayers, ir["default_layer"],

@@ -31,13 +31,13 @@ SMEM_CASES = [
 
 
 @pytest.mark.parametrize("name,size,R,chunks", SMEM_CASES)
-@pytest.mark.parametrize("kernel", ["smem", "generic"])
+@pytest.mark.parametrize("kernel", ["smem", "generic", "warp_hbm"])
 def test_local_smart_parity(name, size, R, chunks, kernel):
     engine = _engine()
     ir, blob, info = load_model(name)
     rates, lut, seeds = make_inputs(ir, info, R, seed=len(name))
     model = engine.Model(ir=ir, blob=blob, info=info)
-    kind = capi.KERNEL_SMEM if kernel == "smem" else capi.KERNEL_GENERIC
+    kind = {"smem": capi.KERNEL_SMEM, "generic": capi.KERNEL_GENERIC, "warp_hbm": capi.KERNEL_WARP_HBM}[kernel]
     batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=kind)
     assert batch.kernel_info()["kernel_name"] == kernel
     gen = run_oracles(blob, size, rates, lut, seeds, chunks)
@@ -96,6 +96,23 @@ def test_otf_parity(name, size, R, chunks):
     for n, oracles in zip(chunks, gen):
         batch.do_steps(n)
         compare_batch(batch, oracles, avail_replicas=(0, R - 1))
+    batch.close()
+
+
+def test_local_smart_lattice_too_large_for_shared_memory():
+    """128x128 cells exceed the 13-bit positions of the compact class entries: the planner falls back to the
+    HBM-resident warp kernel, which must still be bit-exact."""
+    engine = _engine()
+    ir, blob, info = load_model("zgb_local_smart")
+    R, size, n = 6, [128, 128], 3000
+    rates, lut, seeds = make_inputs(ir, info, R, seed=77)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates)
+    assert batch.kernel_info()["kernel_name"] == "warp_hbm"
+    gen = run_oracles(blob, size, rates, lut, seeds, [n])
+    next(gen)
+    batch.do_steps(n)
+    compare_batch(batch, next(gen), avail_replicas=(0, R - 1))
     batch.close()
 
 
