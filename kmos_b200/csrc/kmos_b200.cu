@@ -322,11 +322,12 @@ static void plan_latint(kmos_b200_batch* b) {
     if (m->h.n_proc > 64) return;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, b->device) != cudaSuccess) return;
-    // offsets are applied twice (op cell, then probe inside the decision tree), each |d| <= L
+    // distinct offsets of one event must be distinct cells (the generated code assumes it too: folded probes,
+    // one list operation per (process, cell)): no aliasing under periodic wrap
     for (int i = 0; i < d[8]; ++i) {
         uint32_t w = (uint32_t)d[d[7] + i];
         for (int a = 0; a < m->h.dim; ++a)
-            if (abs((int)(int8_t)((w >> (8 * a)) & 255u)) > b->g.size[a]) return;
+            if (2 * abs((int)(int8_t)((w >> (8 * a)) & 255u)) >= b->g.size[a]) return;
     }
     int Lx = b->g.size[0], LxLy = b->g.size[0] * b->g.size[1];
     if (Lx == 1 || LxLy == 1) return;
