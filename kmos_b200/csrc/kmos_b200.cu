@@ -78,6 +78,7 @@ struct kmos_b200_batch {
     int32_t* d_spec;
     int* d_sched;  // [0] work counter, [1..R] finished epochs per replica (persistent scheduling)
     bool smem_ok;
+    double smem_score;  // resident replicas per SM, discounted by the placement's latency penalty
     std::string smem_reason;
     bool li_ok;  // warp-per-replica lat_int kernel available
     KbLatintParams li;
@@ -437,6 +438,7 @@ static void plan_smem(kmos_b200_batch* b) {
     }
     if (!best_total) { b->smem_reason = "one replica does not fit in shared memory"; return; }
     sp = best;
+    b->smem_score = best_score;
     const char* wenv = getenv("KMOS_B200_WARPS_PER_CTA");
     if (wenv && atoi(wenv) > 0 && sp.tab_bytes + sp.nbt_bytes + atoi(wenv) * sp.rep_bytes <= max_smem) {
         b->wpc = atoi(wenv);
@@ -457,6 +459,19 @@ static void plan_smem(kmos_b200_batch* b) {
     const char* nb = getenv("KMOS_B200_NO_BULK");
     sp.use_bulk = (nb && nb[0] == '1') ? 0 : 1;
     b->smem_ok = true;
+}
+
+// Shared-memory kernel vs HBM-resident warp kernel: measured per-warp speeds are about 1 : 0.65 : 0.26
+// (all-shared : lists in L2 : everything in HBM), so the HBM kernel wins when shared memory can host only a
+// few replicas per SM (ZGB 64x64: 7 vs 24 warps per SM).
+static int auto_kernel(const kmos_b200_batch* b) {
+    if (b->smem_ok && b->li_ok) {
+        double hbm_warps = (double)b->R / (double)(b->sm_count > 0 ? b->sm_count : 1);
+        if (hbm_warps > 24.0) hbm_warps = 24.0;
+        return (0.26 * hbm_warps > b->smem_score) ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_SMEM;
+    }
+    if (b->smem_ok) return KMOS_B200_KERNEL_SMEM;
+    return b->li_ok ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC;
 }
 
 extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32_t size[3], int32_t device,
@@ -531,7 +546,7 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
         CU(cudaMalloc(&b->d_spec, b->spec.size() * 4));
         CU(cudaMemcpy(b->d_spec, b->spec.data(), b->spec.size() * 4, cudaMemcpyHostToDevice));
     }
-    b->kernel = b->smem_ok ? KMOS_B200_KERNEL_SMEM : (b->li_ok ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC);
+    b->kernel = auto_kernel(b);
     *out = b;
     return KMOS_B200_OK;
 }
@@ -551,8 +566,7 @@ extern "C" void kmos_b200_batch_destroy(kmos_b200_batch* b) {
 extern "C" int kmos_b200_batch_volume(const kmos_b200_batch* b) { return b->g.volume; }
 
 extern "C" int kmos_b200_select_kernel(kmos_b200_batch* b, int32_t kind) {
-    if (kind == KMOS_B200_KERNEL_AUTO)
-        kind = b->smem_ok ? KMOS_B200_KERNEL_SMEM : (b->li_ok ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC);
+    if (kind == KMOS_B200_KERNEL_AUTO) kind = auto_kernel(b);
     if (kind == KMOS_B200_KERNEL_SMEM && !b->smem_ok)
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "shared-memory kernel unavailable: " + b->smem_reason);
     if (kind == KMOS_B200_KERNEL_WARP_HBM && !b->li_ok)
