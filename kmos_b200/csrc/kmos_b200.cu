@@ -467,7 +467,7 @@ static void plan_smem(kmos_b200_batch* b) {
 static int auto_kernel(const kmos_b200_batch* b) {
     if (b->smem_ok && b->li_ok) {
         double hbm_warps = (double)b->R / (double)(b->sm_count > 0 ? b->sm_count : 1);
-        if (hbm_warps > 24.0) hbm_warps = 24.0;
+        if (hbm_warps > 32.0) hbm_warps = 32.0;
         return (0.26 * hbm_warps > b->smem_score) ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_SMEM;
     }
     if (b->smem_ok) return KMOS_B200_KERNEL_SMEM;
@@ -771,13 +771,16 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         const int blocks = (b->R + b->li_wpc - 1) / b->li_wpc, threads = b->li_wpc * 32;
         void (*fn)(const KbLatintParams);
         const bool p2l = b->model->h.n_proc > 32;
+        const bool dense = (long long)b->R > 24LL * b->sm_count;  // more replicas than 3 CTAs/SM can hold
+#define KB_LI(PPLV, IDX, MODEV) (dense ? kb_latint_kernel<PPLV, IDX, MODEV, 4> : kb_latint_kernel<PPLV, IDX, MODEV, 3>)
         if (b->li_mode == 0) {
-            if (p2l) fn = b->idx32 ? kb_latint_kernel<2, uint32_t, 0> : kb_latint_kernel<2, uint16_t, 0>;
-            else fn = b->idx32 ? kb_latint_kernel<1, uint32_t, 0> : kb_latint_kernel<1, uint16_t, 0>;
+            if (p2l) fn = b->idx32 ? KB_LI(2, uint32_t, 0) : KB_LI(2, uint16_t, 0);
+            else fn = b->idx32 ? KB_LI(1, uint32_t, 0) : KB_LI(1, uint16_t, 0);
         } else {
-            if (p2l) fn = b->idx32 ? kb_latint_kernel<2, uint32_t, 1> : kb_latint_kernel<2, uint16_t, 1>;
-            else fn = b->idx32 ? kb_latint_kernel<1, uint32_t, 1> : kb_latint_kernel<1, uint16_t, 1>;
+            if (p2l) fn = b->idx32 ? KB_LI(2, uint32_t, 1) : KB_LI(2, uint16_t, 1);
+            else fn = b->idx32 ? KB_LI(1, uint32_t, 1) : KB_LI(1, uint16_t, 1);
         }
+#undef KB_LI
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->li_smem_bytes));
         fn<<<blocks, threads, b->li_smem_bytes, b->stream>>>(li);
         CU(cudaGetLastError());
