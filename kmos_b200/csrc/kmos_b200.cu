@@ -540,8 +540,8 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     b->compact_valid = false;
     b->d_spec = nullptr;
     b->d_sched = nullptr;
+    if (b->smem_ok || b->li_ok) CU(cudaMalloc(&b->d_sched, ((size_t)R + 1) * sizeof(int)));
     if (b->smem_ok) {
-        CU(cudaMalloc(&b->d_sched, ((size_t)R + 1) * sizeof(int)));
         CU(cudaMalloc(&b->image, (size_t)R * b->sp.img_bytes));
         CU(cudaMalloc(&b->d_spec, b->spec.size() * 4));
         CU(cudaMemcpy(b->d_spec, b->spec.data(), b->spec.size() * 4, cudaMemcpyHostToDevice));
@@ -768,7 +768,7 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         li.lattice = b->lattice; li.lat_stride = b->lat_stride; li.nsites = b->nsites; li.p1 = b->p1; li.p2 = b->p2;
         li.plane_elems = b->plane_bytes / (b->idx32 ? 4 : 2);
         li.rates = b->rates; li.integ = b->integ; li.procstat = b->procstat; li.sc = b->sc; li.R = b->R; li.nsteps = n;
-        const int blocks = (b->R + b->li_wpc - 1) / b->li_wpc, threads = b->li_wpc * 32;
+        const int threads = b->li_wpc * 32;
         void (*fn)(const KbLatintParams);
         const bool p2l = b->model->h.n_proc > 32;
         const bool dense = (long long)b->R > 24LL * b->sm_count;  // more replicas than 3 CTAs/SM can hold
@@ -782,6 +782,28 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         }
 #undef KB_LI
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->li_smem_bytes));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, b->li_smem_bytes));
+        if (per_sm < 1) per_sm = 1;
+        int blocks = (b->R + b->li_wpc - 1) / b->li_wpc;
+        if (blocks > per_sm * b->sm_count) blocks = per_sm * b->sm_count;
+        const long long slots = (long long)blocks * b->li_wpc;
+        long long epochs = 1;
+        if (b->R > slots) {
+            epochs = (24 * slots + b->R - 1) / b->R;
+            const long long max_epochs = n / 256 > 0 ? n / 256 : 1;
+            if (epochs > max_epochs) epochs = max_epochs;
+            if (epochs > 64) epochs = 64;
+        }
+        const char* ep_env = getenv("KMOS_B200_EPOCHS");
+        if (ep_env && atoi(ep_env) > 0) epochs = atoi(ep_env);
+        li.chunk = (n + epochs - 1) / epochs;
+        epochs = (n + li.chunk - 1) / li.chunk;
+        if (epochs * (long long)b->R > 0x7fffffffLL) return set_err(KMOS_B200_ERR_ARG, "do_kmc_steps: too many work items");
+        li.n_items = (int)(epochs * b->R);
+        li.work_counter = b->d_sched;
+        li.done = b->d_sched + 1;
+        CU(cudaMemsetAsync(b->d_sched, 0, ((size_t)b->R + 1) * sizeof(int), b->stream));
         fn<<<blocks, threads, b->li_smem_bytes, b->stream>>>(li);
         CU(cudaGetLastError());
         return KMOS_B200_OK;
