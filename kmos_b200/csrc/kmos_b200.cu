@@ -23,6 +23,7 @@
 #include "kb_interp.h"
 #include "kb_smem.cuh"
 #include "kb_latint.cuh"
+#include "kb_otf.cuh"
 
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
@@ -80,6 +81,7 @@ struct kmos_b200_batch {
     bool smem_ok;
     double smem_score;  // resident replicas per SM, discounted by the placement's latency penalty
     std::string smem_reason;
+    bool otf_ok; // warp-per-replica otf kernel available (lane per rates_matrix row)
     bool li_ok;  // warp-per-replica lat_int kernel available
     KbLatintParams li;
     int li_wpc, li_smem_bytes, li_mode;  // li_mode 0: lat_int decision trees, 1: local_smart flattened ops
@@ -311,6 +313,17 @@ static bool specialise_tables(const int32_t* d, int ncells, int cap, std::vector
 static void plan_latint(kmos_b200_batch* b) {
     const kmos_b200_model* m = b->model;
     b->li_ok = false;
+    b->otf_ok = false;
+    if (m->h.backend == KB_BACKEND_OTF) {
+        const int nchunk = (b->g.ncells + KB_OTF_CHUNK - 1) / KB_OTF_CHUNK;
+        cudaDeviceProp prop;
+        if (m->h.n_proc <= 32 && (long long)m->h.n_proc * nchunk <= b->g.ncells &&
+            cudaGetDeviceProperties(&prop, b->device) == cudaSuccess) {
+            b->sm_count = prop.multiProcessorCount;
+            b->otf_ok = true;
+        }
+        return;
+    }
     const int32_t* d = nullptr;
     int dlen = 0;
     if (m->h.backend == KB_BACKEND_LAT_INT && m->h.dev && m->h.dev_len >= 16 && m->h.dev[0] == 3 && m->h.dev[1] == 1) {
@@ -471,7 +484,7 @@ static int auto_kernel(const kmos_b200_batch* b) {
         return (0.26 * hbm_warps > b->smem_score) ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_SMEM;
     }
     if (b->smem_ok) return KMOS_B200_KERNEL_SMEM;
-    return b->li_ok ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC;
+    return (b->li_ok || b->otf_ok) ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC;
 }
 
 extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32_t size[3], int32_t device,
@@ -569,7 +582,7 @@ extern "C" int kmos_b200_select_kernel(kmos_b200_batch* b, int32_t kind) {
     if (kind == KMOS_B200_KERNEL_AUTO) kind = auto_kernel(b);
     if (kind == KMOS_B200_KERNEL_SMEM && !b->smem_ok)
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "shared-memory kernel unavailable: " + b->smem_reason);
-    if (kind == KMOS_B200_KERNEL_WARP_HBM && !b->li_ok)
+    if (kind == KMOS_B200_KERNEL_WARP_HBM && !b->li_ok && !b->otf_ok)
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "warp-per-replica HBM kernel unavailable for this model/lattice");
     if (kind != KMOS_B200_KERNEL_SMEM && kind != KMOS_B200_KERNEL_GENERIC && kind != KMOS_B200_KERNEL_WARP_HBM)
         return set_err(KMOS_B200_ERR_ARG, "bad kernel kind");
@@ -586,6 +599,8 @@ extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[12]) {
         info[7] = (b->R + b->wpc - 1) / b->wpc;
         if (info[7] > (int64_t)b->sm_count * b->ctas_per_sm) info[7] = (int64_t)b->sm_count * b->ctas_per_sm;
         info[8] = b->sp.p1_global; info[9] = b->regs; info[10] = b->sp.split; info[11] = b->sp.img_bytes;
+    } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM && b->otf_ok) {
+        info[1] = 4; info[4] = b->sm_count; info[7] = (b->R + 3) / 4; info[8] = 1;
     } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM) {
         info[1] = b->li_wpc; info[2] = b->li_smem_bytes; info[4] = b->sm_count; info[5] = b->li.rep_bytes;
         info[6] = (int64_t)b->li.dev_words * 4; info[7] = (b->R + b->li_wpc - 1) / b->li_wpc; info[8] = 1;
@@ -760,6 +775,21 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     if (n == 0) return KMOS_B200_OK;
     if (b->kernel == KMOS_B200_KERNEL_GENERIC) return launch_generic(b, KB_MODE_STEPS, n, 0, -1);
     CU(cudaSetDevice(b->device));
+    if (b->kernel == KMOS_B200_KERNEL_WARP_HBM && b->otf_ok) {
+        int rc0 = ensure_canonical(b);
+        if (rc0) return rc0;
+        KbOtfParams op;
+        op.m = b->d; op.g = b->g; op.R = b->R; op.lat_stride = b->lat_stride;
+        op.plane_elems = b->plane_bytes / (b->idx32 ? 4 : 2);
+        op.lattice = b->lattice; op.p1 = b->p1; op.p2 = b->p2; op.nsites = b->nsites; op.rates = b->rates;
+        op.integ = b->integ; op.accum = b->accum; op.procstat = b->procstat; op.sc = b->sc;
+        op.rates_matrix = b->rates_matrix; op.accum_proc = b->accum_proc; op.lut = b->lut; op.nsteps = n;
+        const int threads = 128, blocks = (b->R + 3) / 4;
+        if (b->idx32) kb_otf_kernel<uint32_t><<<blocks, threads, 0, b->stream>>>(op);
+        else kb_otf_kernel<uint16_t><<<blocks, threads, 0, b->stream>>>(op);
+        CU(cudaGetLastError());
+        return KMOS_B200_OK;
+    }
     if (b->kernel == KMOS_B200_KERNEL_WARP_HBM) {
         int rc0 = ensure_canonical(b);
         if (rc0) return rc0;

@@ -72,7 +72,7 @@ def test_config4_pairwise_otf_256x256():
     lut = np.stack([otf_mod.build_lut(ir, info, rates[r]) for r in range(R)])
     seeds = np.arange(R, dtype=np.uint64) + np.uint64(5)
     b = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, [256, 256], seeds=seeds, rates=rates, lut=lut)
-    assert b.kernel_info()["kernel_name"] == "generic"
+    assert b.kernel_info()["kernel_name"] == "warp_hbm"
     b.do_steps(n)
     _check_sample(b, blob, [256, 256], seeds, rates, lut, n, [0, 7], avail=True)
 

@@ -83,14 +83,16 @@ OTF_CASES = [
 ]
 
 
-@pytest.mark.parametrize("name,size,R,chunks", OTF_CASES)
-def test_otf_parity(name, size, R, chunks):
+@pytest.mark.parametrize("name,size,R,chunks", OTF_CASES + [("pairwise_otf_otf", [40, 36], 5, [1500, 1500])])
+@pytest.mark.parametrize("kernel", ["warp_hbm", "generic"])
+def test_otf_parity(name, size, R, chunks, kernel):
     engine = _engine()
     ir, blob, info = load_model(name)
     rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + 1)
     model = engine.Model(ir=ir, blob=blob, info=info)
-    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, lut=lut)
-    assert batch.kernel_info()["kernel_name"] == "generic"
+    kind = capi.KERNEL_WARP_HBM if kernel == "warp_hbm" else capi.KERNEL_GENERIC
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, lut=lut, kernel=kind)
+    assert batch.kernel_info()["kernel_name"] == kernel
     gen = run_oracles(blob, size, rates, lut, seeds, chunks)
     compare_batch(batch, next(gen), avail_replicas=(0,))
     for n, oracles in zip(chunks, gen):
