@@ -17,6 +17,19 @@
 #include "kb_smem.cuh"
 
 #define KB_OTF_CHUNK 64
+#define KB_OTF_RG 4       // rows summed concurrently (one lane each)
+#define KB_OTF_STAGE 128  // entries per row and pipeline stage
+#define KB_OTF_ROWPAD (KB_OTF_STAGE + 2)  // 16 B-aligned rows whose LDS.128 streams fall into disjoint bank groups
+#define KB_OTF_WARP_SMEM (2 * KB_OTF_RG * KB_OTF_ROWPAD * 8)
+
+__device__ __forceinline__ void kb_cp_async8(void* dst_smem, const void* src_gmem, bool pred) {
+    const int sz = pred ? 8 : 0;  // src-size 0: zero fill, no global access
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(kb_smem_addr(dst_smem)), "l"(src_gmem), "r"(sz)
+                 : "memory");
+}
+__device__ __forceinline__ void kb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void kb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct KbOtfParams {
     KbModelView m;
@@ -58,25 +71,70 @@ __global__ void __launch_bounds__(128) kb_otf_kernel(const KbOtfParams prm) {
     r.seed = s0.seed; r.replica = s0.replica; r.status = s0.status;
     for (int i = 0; i < 5; ++i) r.err[i] = s0.err[i];
     KbInterp<idx_t> it(prm.m, prm.g, r);
+    extern __shared__ __align__(16) unsigned char kb_otf_smem[];
+    double* stage_buf = reinterpret_cast<double*>(kb_otf_smem + (size_t)(threadIdx.x >> 5) * KB_OTF_WARP_SMEM);
 
     for (long long step = 0; step < prm.nsteps; ++step) {
         int status = __shfl_sync(KB_FULL, r.status, 0);
         if (status != KB_OK) break;
-        // -- update_accum_rate: lane i owns row i
-        if (lane < P) {
-            double* rm = r.rates_matrix + (size_t)lane * (C + 1);
-            double* marks = r.accum_proc + (size_t)lane * nchunk;
-            const int n = r.nsites[lane];
+        // -- update_accum_rate: rows in groups of KB_OTF_RG; the whole warp streams the group's next stage into
+        //    shared memory with cp.async (coalesced) while lane r < RG adds up the current stage of row g*RG + r
+        //    serially, in the reference's order
+        for (int g0 = 0; g0 < P; g0 += KB_OTF_RG) {
+            const int myrow = g0 + lane;                      // meaningful for lane < RG
+            const bool summer = lane < KB_OTF_RG && myrow < P;
+            const int my_n = summer ? r.nsites[myrow] : 0;
+            int max_n = my_n;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) max_n = max(max_n, __shfl_xor_sync(KB_FULL, max_n, o));
+            const int n_stages = (max_n + KB_OTF_STAGE - 1) / KB_OTF_STAGE;
             double tot = 0.0;
-            int j = 0;
-            for (int c = 0; j + KB_OTF_CHUNK <= n; ++c) {
-#pragma unroll 8
-                for (int k = 0; k < KB_OTF_CHUNK; ++k) tot = __dadd_rn(tot, rm[j + k]);
-                j += KB_OTF_CHUNK;
-                marks[c] = tot;  // = accum_rates_proc(j) of the reference
+            double* marks = r.accum_proc + (size_t)(summer ? myrow : 0) * nchunk;
+            const double* rowp[KB_OTF_RG];  // warp-uniform row bases and lengths (only entries < nsites are read)
+            int rown[KB_OTF_RG];
+#pragma unroll
+            for (int rr = 0; rr < KB_OTF_RG; ++rr) {
+                rowp[rr] = r.rates_matrix + (size_t)(g0 + rr < P ? g0 + rr : 0) * (C + 1);
+                rown[rr] = __shfl_sync(KB_FULL, my_n, rr);
             }
-            for (; j < n; ++j) tot = __dadd_rn(tot, rm[j]);
-            rm[C] = tot;
+            auto issue = [&](int stage) {
+                double* buf = stage_buf + (size_t)(stage & 1) * KB_OTF_RG * KB_OTF_ROWPAD + lane;
+                const int base = stage * KB_OTF_STAGE + lane;
+#pragma unroll
+                for (int rr = 0; rr < KB_OTF_RG; ++rr) {
+#pragma unroll
+                    for (int k = 0; k < KB_OTF_STAGE; k += 32) {
+                        const bool in = base + k < rown[rr];
+                        kb_cp_async8(buf + rr * KB_OTF_ROWPAD + k, in ? rowp[rr] + base + k : r.rates_matrix, in);
+                    }
+                }
+                kb_cp_async_commit();
+            };
+            if (n_stages > 0) issue(0);
+            for (int st = 0; st < n_stages; ++st) {
+                if (st + 1 < n_stages) { issue(st + 1); kb_cp_async_wait<1>(); } else { kb_cp_async_wait<0>(); }
+                __syncwarp();
+                if (summer) {
+                    const double* buf = stage_buf + (size_t)(st & 1) * KB_OTF_RG * KB_OTF_ROWPAD + lane * KB_OTF_ROWPAD;
+                    const int base = st * KB_OTF_STAGE;
+                    const int lim = min(KB_OTF_STAGE, my_n - base);
+                    for (int k0 = 0; k0 < lim; k0 += KB_OTF_CHUNK) {
+                        if (k0 + KB_OTF_CHUNK <= lim) {
+                            const double2* b2 = reinterpret_cast<const double2*>(buf + k0);
+#pragma unroll
+                            for (int k = 0; k < KB_OTF_CHUNK / 2; ++k) {
+                                const double2 v = b2[k];
+                                tot = __dadd_rn(__dadd_rn(tot, v.x), v.y);
+                            }
+                            marks[(base + k0) / KB_OTF_CHUNK] = tot;  // accum_rates_proc(base + k0 + CHUNK)
+                        } else {
+                            for (int k = k0; k < lim; ++k) tot = __dadd_rn(tot, buf[k]);
+                        }
+                    }
+                }
+                __syncwarp();  // the buffer is refilled two stages later
+            }
+            if (summer) r.rates_matrix[(size_t)myrow * (C + 1) + C] = tot;
         }
         __syncwarp();
         if (lane == 0) {

@@ -785,8 +785,9 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         op.integ = b->integ; op.accum = b->accum; op.procstat = b->procstat; op.sc = b->sc;
         op.rates_matrix = b->rates_matrix; op.accum_proc = b->accum_proc; op.lut = b->lut; op.nsteps = n;
         const int threads = 128, blocks = (b->R + 3) / 4;
-        if (b->idx32) kb_otf_kernel<uint32_t><<<blocks, threads, 0, b->stream>>>(op);
-        else kb_otf_kernel<uint16_t><<<blocks, threads, 0, b->stream>>>(op);
+        const int otf_smem = 4 * KB_OTF_WARP_SMEM;
+        if (b->idx32) kb_otf_kernel<uint32_t><<<blocks, threads, otf_smem, b->stream>>>(op);
+        else kb_otf_kernel<uint16_t><<<blocks, threads, otf_smem, b->stream>>>(op);
         CU(cudaGetLastError());
         return KMOS_B200_OK;
     }

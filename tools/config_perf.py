@@ -21,8 +21,17 @@ CONFIGS = [
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="config letters to run, e.g. DE")
+    ap.add_argument("--replicas", type=int, default=0, help="override the replica count")
+    ap.add_argument("--out", default="configs_r1.json")
+    args = ap.parse_args()
     out = []
     for label, name, size, R, n in CONFIGS:
+        if args.only and label[0] not in args.only:
+            continue
+        R = args.replicas or R
         ir = tables.load_ir(os.path.join(REPO, "tests", "golden", "models", name + ".json"))
         m = engine.Model(ir=ir)
         rates = workloads.rates_for(name.split("_")[0], ir, R)
@@ -45,7 +54,7 @@ def main():
                     "all_ok": bool((b.status == 0).all())})
         print(json.dumps(out[-1]), flush=True)
         b.close()
-    with open(os.path.join(REPO, "gpurun_out", "configs_r1.json"), "w") as f:
+    with open(os.path.join(REPO, "gpurun_out", args.out), "w") as f:
         json.dump(out, f, indent=1)
 
 
