@@ -600,7 +600,8 @@ extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[12]) {
         if (info[7] > (int64_t)b->sm_count * b->ctas_per_sm) info[7] = (int64_t)b->sm_count * b->ctas_per_sm;
         info[8] = b->sp.p1_global; info[9] = b->regs; info[10] = b->sp.split; info[11] = b->sp.img_bytes;
     } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM && b->otf_ok) {
-        info[1] = 4; info[4] = b->sm_count; info[7] = (b->R + 3) / 4; info[8] = 1;
+        info[1] = KB_OTF_WARPS; info[2] = KB_OTF_SMEM; info[4] = b->sm_count;
+        info[7] = (b->R + KB_OTF_WARPS - 1) / KB_OTF_WARPS; info[8] = 1;
     } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM) {
         info[1] = b->li_wpc; info[2] = b->li_smem_bytes; info[4] = b->sm_count; info[5] = b->li.rep_bytes;
         info[6] = (int64_t)b->li.dev_words * 4; info[7] = (b->R + b->li_wpc - 1) / b->li_wpc; info[8] = 1;
@@ -784,10 +785,14 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         op.lattice = b->lattice; op.p1 = b->p1; op.p2 = b->p2; op.nsites = b->nsites; op.rates = b->rates;
         op.integ = b->integ; op.accum = b->accum; op.procstat = b->procstat; op.sc = b->sc;
         op.rates_matrix = b->rates_matrix; op.accum_proc = b->accum_proc; op.lut = b->lut; op.nsteps = n;
-        const int threads = 128, blocks = (b->R + 3) / 4;
-        const int otf_smem = 4 * KB_OTF_WARP_SMEM;
-        if (b->idx32) kb_otf_kernel<uint32_t><<<blocks, threads, otf_smem, b->stream>>>(op);
-        else kb_otf_kernel<uint16_t><<<blocks, threads, otf_smem, b->stream>>>(op);
+        const int threads = 32 * KB_OTF_WARPS, blocks = (b->R + KB_OTF_WARPS - 1) / KB_OTF_WARPS;
+        if (b->idx32) {
+            CU(cudaFuncSetAttribute(kb_otf_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_OTF_SMEM));
+            kb_otf_kernel<uint32_t><<<blocks, threads, KB_OTF_SMEM, b->stream>>>(op);
+        } else {
+            CU(cudaFuncSetAttribute(kb_otf_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_OTF_SMEM));
+            kb_otf_kernel<uint16_t><<<blocks, threads, KB_OTF_SMEM, b->stream>>>(op);
+        }
         CU(cudaGetLastError());
         return KMOS_B200_OK;
     }

@@ -16,7 +16,7 @@ CONFIGS = [
     ("B ZGB 64x64, local_smart", "zgb_local_smart", [64, 64], 4096, 4000),
     ("C RuO2 CO oxidation 20x20, local_smart", "ruo2_local_smart", [20, 20], 16384, 5000),
     ("D pairwise interaction 128x128, lat_int", "pairwise_lat_int", [128, 128], 2048, 4000),
-    ("E pairwise interaction 256x256, otf", "pairwise_otf_otf", [256, 256], 1184, 40),
+    ("E pairwise interaction 256x256, otf", "pairwise_otf_otf", [256, 256], 3552, 40),
 ]
 
 
