@@ -282,7 +282,7 @@ struct KbCellCtx {
 //   w1 = class base (cls * ncells) | first slot of the list (arena*cap, or arena*cap + cap-1 if it grows down) << 16
 //   then ncond probe words off_id | n<<5 | mask<<8
 template <int PPL, int NCOND, bool SPLIT, bool P1G, bool NBT>
-__global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemParams prm) {
+__global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemParams prm) {
     extern __shared__ __align__(128) unsigned char kb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
@@ -351,6 +351,13 @@ __global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemPa
     // touched ~10x per step while plane 2 and the lattice take ~40 probes, so keeping only the latter in
     // shared memory trades a few L2 round trips per step for 2-3x more resident replicas per SM
     unsigned char* p1 = P1G ? g_img : base;
+    if (P1G) {
+        // keep the replica's list base in registers: ptxas otherwise re-derives it (64-bit multiply of the
+        // replica index) in every round to stay under the register cap
+        unsigned long long p1v = reinterpret_cast<unsigned long long>(p1);
+        asm volatile("" : "+l"(p1v));
+        p1 = reinterpret_cast<unsigned char*>(p1v);
+    }
     unsigned char* p1hi = p1 + prm.off_hi;
     unsigned char* g_stage = g_img + prm.stage_off;
     uint8_t* g_lat = prm.lattice + (size_t)rep * prm.lat_stride;
@@ -386,13 +393,12 @@ __global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemPa
     long long ps0 = has0 ? prm.procstat[(size_t)rep * P + q0] : 0;
     long long ps1 = has1 ? prm.procstat[(size_t)rep * P + q1] : 0;
 
-    KbScalars sc = prm.sc[rep];
-    double kmc_time = sc.kmc_time, kmc_dt = sc.kmc_time_step;
-    long long kmc_step = sc.kmc_step;
-    int status = sc.status;
-    int err0 = 0, err1 = 0, err2 = 0, err3 = 0, err4 = 0;
-
-    const uint32_t k0 = (uint32_t)sc.seed, k1 = (uint32_t)(sc.seed >> 32);
+    KbScalars* const scp = prm.sc + rep;  // only the fields that change are kept in registers / written back
+    double kmc_time = scp->kmc_time, kmc_dt = scp->kmc_time_step;
+    long long kmc_step = scp->kmc_step;
+    int status = scp->status;
+    const uint32_t replica_id = scp->replica;
+    const uint32_t k0 = (uint32_t)scp->seed, k1 = (uint32_t)(scp->seed >> 32);
     const uint32_t my_off = lane < n_off ? offsets[lane] : 0u;
     const int len1 = min(P, 32), len2 = max(P - 32, 0);
     double* Z1 = prodS;       // [len1 zeros][x_0 .. x_{len1-1}] (64 doubles reserved)
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemPa
             // 16 steps of uniforms at once: lane l serves step kmc_step + l/2, Philox slot l&1
             const unsigned long long st = (unsigned long long)kmc_step + (unsigned)(lane >> 1);
             uint32_t rnd[4];
-            kb_philox4x32_10((uint32_t)st, (uint32_t)(st >> 32), sc.replica, (uint32_t)(lane & 1), k0, k1, rnd);
+            kb_philox4x32_10((uint32_t)st, (uint32_t)(st >> 32), replica_id, (uint32_t)(lane & 1), k0, k1, rnd);
             const double u0 = (double)(((((uint64_t)rnd[1] << 32) | rnd[0]) >> 11) + (uint64_t)((lane & 1) ^ 1)) * 0x1.0p-53;
             const double u1 = (double)((((uint64_t)rnd[3] << 32) | rnd[2]) >> 11) * 0x1.0p-53;
             rng_a = (lane & 1) ? u0 : -log(u0);  // odd: ran_site in [0,1); even: -log(ran_time), ran_time in (0,1]
@@ -433,8 +439,13 @@ __global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemPa
         double acc0 = 0.0;
         {
             const double* src = Z1 + lane + 1;
+            if (len1 == 32) {  // the common full-warp case, completely unrolled
+#pragma unroll
+                for (int t = 0; t < 32; ++t) acc0 = __dadd_rn(acc0, src[t]);
+            } else {
 #pragma unroll 4
-            for (int t = 0; t < len1; ++t) acc0 = __dadd_rn(acc0, src[t]);
+                for (int t = 0; t < len1; ++t) acc0 = __dadd_rn(acc0, src[t]);
+            }
         }
         double acc1 = 0.0;
         if (PPL == 2) {
@@ -493,22 +504,34 @@ __global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemPa
                 const int found = lat[idx], oldsp = (int)((w >> 8) & 15u), newsp = (int)((w >> 12) & 15u);
                 if (found != oldsp) {  // replace_species consistency check (base.mpy:1205)
                     status = KB_SPECIES_MISMATCH;
-                    err0 = oldsp; err1 = newsp; err2 = found; err3 = idx + 1; err4 = (int)(kmc_step - 1);
                 } else {
                     lat[idx] = (uint8_t)newsp;
                 }
             }
         }
-        int start = 0;
         const unsigned long long ends = ((unsigned long long)eh.z << 32) | eh.y;
+        // Software pipeline over the rounds: the op words of round r+1 (read-only tables) and the cells they
+        // name are fetched while round r's list updates are in flight; only nr_of_sites, the class entries
+        // and the lists themselves have to wait for the __syncwarp between rounds.
+        int endr = n_rounds > 0 ? (int)(ends & 255u) : 0;
+        bool valid = lane < endr;
+        const uint32_t* op = ops + (ops_start + lane) * STRIDE;
+        uint32_t h = valid ? op[0] : 0u, h1 = valid ? op[1] : 0u;
+        uint32_t cw[NCOND > 0 ? NCOND : 1];
+#pragma unroll
+        for (int j = 0; j < NCOND; ++j) cw[j] = (valid && j < (int)((h >> 1) & 7u)) ? op[2 + j] : 0u;
+        int ca = __shfl_sync(KB_FULL, nb, (int)((h >> 4) & 31u));
         for (int r = 0; r < n_rounds; ++r) {
-            const int endr = (int)((ends >> (8 * r)) & 255u);
-            const int i = start + lane;
-            const bool valid = i < endr;
-            const uint32_t* op = ops + (ops_start + i) * STRIDE;
-            const uint32_t h = valid ? op[0] : 0u;
-            const uint32_t h1 = valid ? op[1] : 0u;
-            const int ca = __shfl_sync(KB_FULL, nb, (int)((h >> 4) & 31u));
+            // -- fetch round r+1
+            const bool more = r + 1 < n_rounds;
+            const int end_n = more ? (int)((ends >> (8 * (r + 1))) & 255u) : endr;
+            const bool valid_n = more && endr + lane < end_n;
+            const uint32_t* op_n = ops + (ops_start + endr + lane) * STRIDE;
+            const uint32_t h_n = valid_n ? op_n[0] : 0u, h1_n = valid_n ? op_n[1] : 0u;
+            uint32_t cw_n[NCOND > 0 ? NCOND : 1];
+#pragma unroll
+            for (int j = 0; j < NCOND; ++j) cw_n[j] = valid_n ? op_n[2 + j] : 0u;
+            // -- round r
             bool ok = valid;
             const int ncond = (int)((h >> 1) & 7u);
             const int q = (int)((h >> 9) & 63u);
@@ -527,11 +550,10 @@ __global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemPa
             }
 #pragma unroll
             for (int j = 0; j < NCOND; ++j) {
-                const uint32_t cw = (valid && j < ncond) ? op[2 + j] : 0u;
-                const int ccell = __shfl_sync(KB_FULL, nb, (int)(cw & 31u));
+                const int ccell = __shfl_sync(KB_FULL, nb, (int)(cw[j] & 31u));
                 if (valid && j < ncond) {
-                    const uint32_t sp = lat[ccell * spuck + (int)((cw >> 5) & 7u) - 1];
-                    ok = ok && (((cw >> 8) >> sp) & 1u);
+                    const uint32_t sp = lat[ccell * spuck + (int)((cw[j] >> 5) & 7u) - 1];
+                    ok = ok && (((cw[j] >> 8) >> sp) & 1u);
                 }
             }
             if (ok) {
@@ -557,12 +579,31 @@ __global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemPa
                     }
                 }
             }
+            // -- rotate
+            ca = __shfl_sync(KB_FULL, nb, (int)((h_n >> 4) & 31u));
+            h = h_n; h1 = h1_n; valid = valid_n; endr = end_n;
+#pragma unroll
+            for (int j = 0; j < NCOND; ++j) cw[j] = cw_n[j];
             __syncwarp();
-            start = endr;
         }
         __syncwarp();  // lattice writes of an event without ops must be visible to the next step
         // a lane-local failure (species mismatch / capacity) stops the replica for every lane
-        if (__any_sync(KB_FULL, status != KB_OK)) status = __reduce_max_sync(KB_FULL, status);
+        if (__any_sync(KB_FULL, status != KB_OK)) {
+            const unsigned mm = __ballot_sync(KB_FULL, status == KB_SPECIES_MISMATCH);
+            if (mm) {
+                // error tuple of the first failing replace_species call (old, new, found, site, step), rebuilt
+                // here so that the step loop carries no registers for it; the lattice site was left untouched
+                const int src = __ffs(mm) - 1;
+                const uint32_t w = reinterpret_cast<const uint32_t*>(events + 2 * pidx + 1)[src];
+                const int wcell = __shfl_sync(KB_FULL, nb, (int)(w & 31u));
+                if (lane == 0) {
+                    const int idx = wcell * spuck + (int)((w >> 5) & 7u) - 1;
+                    scp->err[0] = (int)((w >> 8) & 15u); scp->err[1] = (int)((w >> 12) & 15u);
+                    scp->err[2] = lat[idx]; scp->err[3] = idx + 1; scp->err[4] = (int)kmc_step;
+                }
+            }
+            status = __reduce_max_sync(KB_FULL, status);
+        }
     }
     status = __reduce_max_sync(KB_FULL, status);
 
@@ -588,19 +629,8 @@ __global__ void __launch_bounds__(P1G ? 896 : 640) kb_smem_kernel(const KbSmemPa
     for (int i = lane; i < P; i += 32) g_ns[i] = nS[i];
     if (has0) { prm.integ[(size_t)rep * P + q0] = integ0; prm.procstat[(size_t)rep * P + q0] = ps0; }
     if (has1) { prm.integ[(size_t)rep * P + q1] = integ1; prm.procstat[(size_t)rep * P + q1] = ps1; }
-    // the failing lane (if any) owns the error tuple
-    const unsigned bad = __ballot_sync(KB_FULL, err3 != 0);
-    if (bad) {
-        const int src = __ffs(bad) - 1;
-        err0 = __shfl_sync(KB_FULL, err0, src); err1 = __shfl_sync(KB_FULL, err1, src);
-        err2 = __shfl_sync(KB_FULL, err2, src); err3 = __shfl_sync(KB_FULL, err3, src);
-        err4 = __shfl_sync(KB_FULL, err4, src);
-    }
     if (lane == 0) {
-        KbScalars out = sc;
-        out.kmc_time = kmc_time; out.kmc_time_step = kmc_dt; out.kmc_step = kmc_step; out.status = status;
-        if (bad) { out.err[0] = err0; out.err[1] = err1; out.err[2] = err2; out.err[3] = err3; out.err[4] = err4; }
-        prm.sc[rep] = out;
+        scp->kmc_time = kmc_time; scp->kmc_time_step = kmc_dt; scp->kmc_step = kmc_step; scp->status = status;
     }
     // publish: everything this warp wrote for the replica is visible before the epoch counter moves
     __threadfence();

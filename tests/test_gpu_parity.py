@@ -163,6 +163,38 @@ def test_deadlock_is_a_status_not_a_hang():
     assert np.all(batch.lattice == 0)  # CO everywhere (species sorted by name: CO=0, empty=1)
 
 
+def test_species_mismatch_reports_the_reference_error_tuple():
+    """replace_species finds another species than the rule expects: the reference prints (old, new, found, site,
+    step) and stops (base.mpy:1205-1228; KMC_Model.post_mortem reads the tuple).  A deliberately inconsistent
+    rule set (take_CO expects 'empty' where its condition guarantees CO) must stop every replica at its first
+    desorption with the oracle's tuple, on every kernel."""
+    import copy
+    from kmos_b200 import tables
+    from oracle import oracle
+    engine = _engine()
+    ir, _blob, _info = load_model("mini_101_local_smart")
+    ir = copy.deepcopy(ir)
+    ir["routines"]["take_CO_simple_cubic_hollow"][0] = ["replace", [0, 0, 0, 0], 1, 1]
+    blob, info = tables.build_blob(ir)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    R, size = 6, [6, 5]
+    seeds = np.arange(R, dtype=np.uint64) + np.uint64(3)
+    rates = np.tile(np.array([100.0, 100.0]), (R, 1))
+    for kind in (capi.KERNEL_SMEM, capi.KERNEL_WARP_HBM, capi.KERNEL_GENERIC):
+        batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=kind)
+        batch.do_steps(200)
+        status, err, step, lat = batch.status, batch.error_info, batch.kmc_step, batch.lattice
+        for r in range(R):
+            o = oracle.Oracle(blob, size, seed=int(seeds[r]), replica=r, rates=rates[r])
+            assert o.do_steps(200) == capi.REPLICA_SPECIES_MISMATCH
+            ost, oerr = o.status
+            assert status[r] == ost == capi.REPLICA_SPECIES_MISMATCH, (kind, r)
+            assert list(err[r]) == list(oerr), (kind, r, err[r], oerr)
+            assert step[r] == o.kmc_step
+            assert np.array_equal(lat[r], o.lattice)
+        batch.close()
+
+
 def test_philox_hook_matches_oracle():
     from oracle import oracle
     L = capi.lib()
