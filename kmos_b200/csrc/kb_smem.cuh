@@ -400,9 +400,11 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
     const uint32_t replica_id = scp->replica;
     const uint32_t k0 = (uint32_t)scp->seed, k1 = (uint32_t)(scp->seed >> 32);
     const uint32_t my_off = lane < n_off ? offsets[lane] : 0u;
-    const int len1 = min(P, 32), len2 = max(P - 32, 0);
-    double* Z1 = prodS;       // [len1 zeros][x_0 .. x_{len1-1}] (64 doubles reserved)
-    double* Z2 = prodS + 64;  // [len2 zeros][x_32 ..]           (64 doubles reserved)
+    // chain lengths padded to a multiple of 2: the extra leading zeros are exact and the unrolled loops need
+    // no remainder
+    const int len1 = (min(P, 32) + 1) & ~1, len2 = (max(P - 32, 0) + 1) & ~1;
+    double* Z1 = prodS;       // [len1 zeros][x_0 .. ]  (64 doubles reserved)
+    double* Z2 = prodS + 64;  // [len2 zeros][x_32 ..]  (64 doubles reserved)
     for (int i = lane; i < 128; i += 32) prodS[i] = 0.0;
     __syncwarp();
     const int lastp = P - 1;
@@ -443,16 +445,14 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
 #pragma unroll
                 for (int t = 0; t < 32; ++t) acc0 = __dadd_rn(acc0, src[t]);
             } else {
-#pragma unroll 4
-                for (int t = 0; t < len1; ++t) acc0 = __dadd_rn(acc0, src[t]);
+                for (int t = 0; t < len1; t += 2) acc0 = __dadd_rn(__dadd_rn(acc0, src[t]), src[t + 1]);
             }
         }
         double acc1 = 0.0;
         if (PPL == 2) {
             acc1 = __shfl_sync(KB_FULL, acc0, 31);  // accum_rates(32)
             const double* src = Z2 + lane + 1;
-#pragma unroll 4
-            for (int t = 0; t < len2; ++t) acc1 = __dadd_rn(acc1, src[t]);
+            for (int t = 0; t < len2; t += 2) acc1 = __dadd_rn(__dadd_rn(acc1, src[t]), src[t + 1]);
         }
         const double total = __shfl_sync(KB_FULL, (PPL == 2 && lastp >= 32) ? acc1 : acc0, lastp & 31);
         if (!(total > 0.0)) { status = KB_DEADLOCK; break; }
