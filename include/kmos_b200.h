@@ -110,6 +110,14 @@ int kmos_b200_set_configuration(kmos_b200_batch *b, int32_t replica, const int32
  * batch's stream; getters synchronise. */
 int kmos_b200_do_kmc_steps(kmos_b200_batch *b, int64_t n);
 int kmos_b200_synchronize(kmos_b200_batch *b);
+/* proclist.get_next_kmc_step(proc, site) (proclist_generic_subroutines.mpy:85-110) for every replica: the next
+ * step's (process, site number), both 1-based, without executing it or advancing the clock; as in the
+ * reference the site is selected with ran_time.  proc[R], site[R]; 0/0 for a dead-locked replica. */
+int kmos_b200_get_next_kmc_step(kmos_b200_batch *b, int32_t *proc, int32_t *site);
+/* proclist.run_proc_nr(proc, nr_site) (generated; kmos/io/__init__.py:305-465): increment_procstat + the
+ * event's rule code on replica r for (proc[r], site[r]); proc[r] = 0 skips the replica.  No random numbers, no
+ * clock update (KMC_Model.run_proc_nr, kmos/run/__init__.py:1357; replay loop of tests/test_run/test_run.py). */
+int kmos_b200_run_proc_nr(kmos_b200_batch *b, const int32_t *proc, const int32_t *site);
 /* Run the batch on a caller-owned CUDA stream (cudaStream_t as void*, e.g. torch's current stream) so that
  * the caller's events and collectives order against the engine's kernels.  NULL restores the own stream. */
 int kmos_b200_batch_set_stream(kmos_b200_batch *b, void *cuda_stream);

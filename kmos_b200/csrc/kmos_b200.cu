@@ -178,10 +178,11 @@ __device__ __forceinline__ void kb_store_replica(const KbBatchView& b, int rep, 
     b.sc[rep] = s;
 }
 
-enum { KB_MODE_STEPS = 0, KB_MODE_INIT = 1, KB_MODE_ADJUST = 2, KB_MODE_ACCUM = 3 };
+enum { KB_MODE_STEPS = 0, KB_MODE_INIT = 1, KB_MODE_ADJUST = 2, KB_MODE_ACCUM = 3, KB_MODE_NEXT = 4, KB_MODE_RUNPROC = 5 };
 
 template <typename idx_t>
-__global__ void kb_generic_kernel(const KbBatchView b, int mode, long long n, int layer, int only_rep) {
+__global__ void kb_generic_kernel(const KbBatchView b, int mode, long long n, int layer, int only_rep,
+                                  int32_t* io_proc, int32_t* io_site) {
     int rep = blockIdx.x * blockDim.x + threadIdx.x;
     if (rep >= b.R) return;
     if (only_rep >= 0 && rep != only_rep) return;
@@ -191,7 +192,26 @@ __global__ void kb_generic_kernel(const KbBatchView b, int mode, long long n, in
     if (mode == KB_MODE_STEPS) it.do_kmc_steps(n);
     else if (mode == KB_MODE_INIT) it.init_state(layer);
     else if (mode == KB_MODE_ADJUST) it.adjust_database(layer);
-    else it.update_accum_rate();
+    else if (mode == KB_MODE_NEXT) {
+        // get_next_kmc_step (proclist_generic_subroutines.mpy:85-110): the step's uniforms, no clock update,
+        // and -- as in the reference -- ran_time is what selects the site
+        double ran_time, ran_proc, ran_site;
+        kb_philox_step(r.seed, r.replica, (uint64_t)r.kmc_step, &ran_time, &ran_proc, &ran_site);
+        it.update_accum_rate();
+        int proc = 0, cell = 0;
+        io_proc[rep] = 0; io_site[rep] = 0;
+        if (r.status == KB_OK && r.accum[b.m.n_proc - 1] > 0. && it.determine_procsite(ran_proc, ran_time, &proc, &cell)) {
+            io_proc[rep] = proc;
+            io_site[rep] = b.m.spuck * cell + it.anchor_n(proc);
+        } else if (r.status == KB_OK) {
+            it.fail(KB_DEADLOCK);
+        }
+    } else if (mode == KB_MODE_RUNPROC) {
+        // run_proc_nr(proc, nr_site): procstat + the event; no random numbers, no clock
+        const int proc = io_proc[rep], site = io_site[rep];
+        if (proc >= 1 && proc <= b.m.n_proc && site >= 1 && site <= b.g.volume && r.status == KB_OK)
+            it.run_proc_nr(proc, (site - 1) / b.m.spuck);
+    } else it.update_accum_rate();
     kb_store_replica(b, rep, r);
 }
 
@@ -734,15 +754,16 @@ static int ensure_compact(kmos_b200_batch* b) {
     return KMOS_B200_OK;
 }
 
-static int launch_generic(kmos_b200_batch* b, int mode, long long n, int layer, int only_rep) {
+static int launch_generic(kmos_b200_batch* b, int mode, long long n, int layer, int only_rep,
+                          int32_t* io_proc = nullptr, int32_t* io_site = nullptr) {
     CU(cudaSetDevice(b->device));
     int rc = ensure_canonical(b);
     if (rc) return rc;
     KbBatchView v = batch_view(b);
     const int threads = 64;
     const int blocks = (b->R + threads - 1) / threads;
-    if (b->idx32) kb_generic_kernel<uint32_t><<<blocks, threads, 0, b->stream>>>(v, mode, n, layer, only_rep);
-    else kb_generic_kernel<uint16_t><<<blocks, threads, 0, b->stream>>>(v, mode, n, layer, only_rep);
+    if (b->idx32) kb_generic_kernel<uint32_t><<<blocks, threads, 0, b->stream>>>(v, mode, n, layer, only_rep, io_proc, io_site);
+    else kb_generic_kernel<uint16_t><<<blocks, threads, 0, b->stream>>>(v, mode, n, layer, only_rep, io_proc, io_site);
     CU(cudaGetLastError());
     return KMOS_B200_OK;
 }
@@ -769,6 +790,38 @@ extern "C" int kmos_b200_set_configuration(kmos_b200_batch* b, int32_t replica, 
         }
     CU(cudaMemcpy(b->lattice + (size_t)r0 * b->lat_stride, lat.data(), lat.size(), cudaMemcpyHostToDevice));
     return launch_generic(b, KB_MODE_ADJUST, 0, layer, replica);
+}
+
+// proclist.get_next_kmc_step / run_proc_nr for every replica (debugging and replay interface of the reference:
+// KMC_Model.get_next_kmc_step / run_proc_nr, kmos/run/__init__.py:1357-1368; tests/test_run/test_run.py)
+static int step_io(kmos_b200_batch* b, int mode, int32_t* proc, int32_t* site, bool to_device, bool to_host) {
+    if (!proc || !site) return set_err(KMOS_B200_ERR_ARG, "proc/site arrays must not be NULL");
+    CU(cudaSetDevice(b->device));
+    int32_t* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)b->R * 2 * sizeof(int32_t)));
+    int rc = KMOS_B200_OK;
+    if (to_device) {
+        if (cudaMemcpyAsync(d, proc, (size_t)b->R * 4, cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d + b->R, site, (size_t)b->R * 4, cudaMemcpyHostToDevice, b->stream) != cudaSuccess)
+            rc = set_err(KMOS_B200_ERR_CUDA, "step_io: host to device copy failed");
+    }
+    if (!rc) rc = launch_generic(b, mode, 0, 0, -1, d, d + b->R);
+    if (!rc && to_host) {
+        if (cudaMemcpyAsync(proc, d, (size_t)b->R * 4, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess ||
+            cudaMemcpyAsync(site, d + b->R, (size_t)b->R * 4, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess)
+            rc = set_err(KMOS_B200_ERR_CUDA, "step_io: device to host copy failed");
+    }
+    cudaStreamSynchronize(b->stream);
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int kmos_b200_get_next_kmc_step(kmos_b200_batch* b, int32_t* proc, int32_t* site) {
+    return step_io(b, KB_MODE_NEXT, proc, site, false, true);
+}
+
+extern "C" int kmos_b200_run_proc_nr(kmos_b200_batch* b, const int32_t* proc, const int32_t* site) {
+    return step_io(b, KB_MODE_RUNPROC, const_cast<int32_t*>(proc), const_cast<int32_t*>(site), true, false);
 }
 
 extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {

@@ -129,6 +129,18 @@ class Batch(object):
     def do_steps(self, n):
         capi.check(self.L.kmos_b200_do_kmc_steps(self.h, int(n)))
 
+    def get_next_kmc_step(self):
+        """proclist.get_next_kmc_step for every replica -> (proc[R], site[R]), 1-based, nothing executed."""
+        proc, site = np.zeros(self.R, np.int32), np.zeros(self.R, np.int32)
+        capi.check(self.L.kmos_b200_get_next_kmc_step(self.h, proc, site))
+        return proc, site
+
+    def run_proc_nr(self, proc, site):
+        """proclist.run_proc_nr(proc[r], site[r]) on every replica (scalars are broadcast; proc 0 skips)."""
+        proc = np.ascontiguousarray(np.broadcast_to(np.asarray(proc, np.int32), (self.R,)))
+        site = np.ascontiguousarray(np.broadcast_to(np.asarray(site, np.int32), (self.R,)))
+        capi.check(self.L.kmos_b200_run_proc_nr(self.h, proc, site))
+
     def set_stream(self, cuda_stream):
         """Run on a caller-owned CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
         capi.check(self.L.kmos_b200_batch_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))

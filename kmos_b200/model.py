@@ -127,6 +127,16 @@ class KMC_Model(object):
         """proclist.do_kmc_steps(n) on every replica (kmos/run/__init__.py:416-432)."""
         self.batch.do_steps(int(n))
 
+    def get_next_kmc_step(self):
+        """KMC_Model.get_next_kmc_step (kmos/run/__init__.py:1365-1368): (proc, site) of replica 0, 1-based."""
+        proc, site = self.batch.get_next_kmc_step()
+        return int(proc[0]), int(site[0])
+
+    def run_proc_nr(self, proc, site):
+        """KMC_Model.run_proc_nr (kmos/run/__init__.py:1357-1363): execute process `proc` on site number `site`
+        (both 1-based) on every replica of the batch."""
+        self.batch.run_proc_nr(proc, site)
+
     # ---- observables ---------------------------------------------------------------------------------------
     def _adjustable(self):
         return [k for k in sorted(self.ir["parameters"]) if self.ir["parameters"][k].get("adjustable")]
@@ -287,5 +297,6 @@ class KMC_Model(object):
             deallocate_system=self.deallocate)
         self.proclist = _Namespace(
             do_kmc_steps=self.do_steps, do_kmc_step=lambda: self.do_steps(1), nr_of_proc=self.model.n_proc,
+            get_next_kmc_step=self.get_next_kmc_step, run_proc_nr=self.run_proc_nr,
             nr_of_species=self.model.n_species, backend=self.ir["backend"],
             get_occupation=lambda: b.occupation[0], **dict(list(nr.items()) + list(sp.items())))

@@ -241,3 +241,48 @@ def test_full_size_ruo2_batch_properties():
     tall = batch.split_tally(batch.reduce_tallies(groups, 16))
     assert np.array_equal(tall["procstat"].sum(axis=0), ps.sum(axis=0).astype(np.float64))
     assert np.all(tall["n_replicas"] == 1024) and np.all(tall["kmc_steps"] == 1024 * n)
+
+
+def test_reference_golden_trajectory_replayed_on_the_gpu():
+    """The reference's own known-answer trajectory (tests/test_run/ref_procs_sites_local_smart.log: 10 000
+    (proc, site) events of the AB model, 20x20) is executed on the GPU through the reference's replay interface
+    (model.run_proc_nr(proc, site), tests/test_run/test_run.py:51-53): every event must be enabled on the GPU
+    when it is due, and lattice, nr_of_sites and both planes of avail_sites must follow the oracle replaying the
+    same log.  Afterwards the batch continues on the shared-memory kernel (canonical -> compact repack)."""
+    import os
+    from conftest import GOLDEN
+    from kmos_b200 import rates as rates_mod
+    from oracle import oracle
+    engine = _engine()
+    ref = np.load(os.path.join(GOLDEN, "ab_ref_procs_sites.npy"))
+    ir, blob, info = load_model("ab_local_smart")
+    r = np.asarray(rates_mod.model_rates(ir))
+    R = 2
+    batch = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, [20, 20], seeds=np.array([1, 2], np.uint64),
+                         rates=np.tile(r, (R, 1)))
+    o = oracle.Oracle(blob, [20, 20], seed=1, replica=0, rates=r)
+    V, P = batch.volume, len(ir["procs"])
+    for i, (proc, site) in enumerate(ref):
+        if i % 1000 == 0 or i == len(ref) - 1:
+            av = batch.avail_sites(1)
+            assert np.array_equal(av, o.avail_sites), "avail_sites differ before event %d" % i
+            assert av.reshape(P, V, 2)[proc - 1, site - 1, 1] != 0, "event %d is not enabled on the GPU" % i
+        batch.run_proc_nr(int(proc), int(site))
+        o.run_proc_nr(int(proc), int(site))
+    assert np.all(batch.status == 0) and np.all(batch.kmc_step == 0)
+    for rep in range(R):
+        assert np.array_equal(batch.lattice[rep], o.lattice)
+        assert np.array_equal(batch.procstat[rep], o.procstat)
+        assert np.array_equal(batch.nr_of_sites[rep], o.nr_of_sites)
+        assert np.array_equal(batch.avail_sites(rep), o.avail_sites)
+    assert batch.procstat[0].sum() == len(ref)
+    # get_next_kmc_step agrees with the oracle's (same Philox draw, site selected with ran_time), then both step
+    gp, gs = batch.get_next_kmc_step()
+    op_, os_, st = o.get_next_kmc_step()
+    assert st == 0 and (int(gp[0]), int(gs[0])) == (op_, os_)
+    batch.select_kernel(capi.KERNEL_SMEM)
+    batch.do_steps(2000)
+    o.do_steps(2000)
+    assert np.array_equal(batch.lattice[0], o.lattice)
+    assert np.array_equal(batch.avail_sites(0), o.avail_sites)
+    np.testing.assert_allclose(batch.kmc_time[0], o.kmc_time, rtol=1e-12)
