@@ -181,7 +181,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(grid, args, extra=None):
@@ -361,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        _emit(line)
     batch.close()
     if world > 1:
         dist.destroy_process_group()
@@ -389,5 +389,15 @@ def main():
         run_ours(args, rank, world, local_rank)
 
 
+def _emit(line):
+    """The one JSON line of the contract goes to the process' original stdout."""
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    # Libraries (NCCL with NCCL_DEBUG=VERSION/INFO in the environment, torch warnings) print to fd 1; the
+    # contract is exactly one JSON line on stdout, so everything else is sent to stderr.
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     main()
