@@ -115,3 +115,36 @@ def test_production_stream_statistics_within_3_sigma():
     ok = (np.abs(diff) <= 3 * sigma) | (sigma == 0)
     assert ok.all(), (diff, sigma)
     assert gpu[:, -1].mean() > 0  # the reactive window: CO2 is produced
+
+
+def test_long_validation_ruo2_256_replicas_1e6_steps():
+    """SURVEY 8d correctness gate: >= 256 replicas, >= 1e6 kMC steps each, checked every 1e5 steps -- lattice and
+    procstat bit-exact, kmc_time within 1e-12 relative -- on the headline configuration (RuO2 20x20, sweep
+    points spread over the T x p_CO grid), against the oracle on all host cores."""
+    import os
+    from kmos_b200 import engine
+    from util import oracle_checkpoints
+    ir, blob, info = load_model("ruo2_local_smart")
+    R, chunks = 256, [100000] * 10
+    grid = workloads.rates_for("ruo2", ir, 16384)
+    rates = np.ascontiguousarray(grid[:: 16384 // R][:R])
+    seeds = np.arange(R, dtype=np.uint64) * np.uint64(104729) + np.uint64(17)
+    b = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, [20, 20], seeds=seeds, rates=rates)
+    assert b.kernel_info()["kernel_name"] == "smem"
+    got = []
+    for n in chunks:
+        b.do_steps(n)
+        got.append((b.lattice.astype(np.int8), b.procstat, b.kmc_time, b.kmc_step, b.status))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    olat, ops, ot, ostep, ost = oracle_checkpoints(blob, [20, 20], seeds, rates, chunks, cores)
+    for c in range(len(chunks)):
+        lat, ps, t, step, st = got[c]
+        assert np.all(st == 0) and np.all(ost[:, c] == 0)
+        assert np.all(step == sum(chunks[: c + 1])) and np.all(ostep[:, c] == step)
+        bad = np.nonzero((lat != olat[:, c]).any(axis=1))[0]
+        assert bad.size == 0, "lattice differs, checkpoint %d, replicas %s" % (c, bad[:8])
+        assert np.array_equal(ps, ops[:, c]), "procstat differs, checkpoint %d" % c
+        np.testing.assert_allclose(t, ot[:, c], rtol=1e-12, atol=0)

@@ -45,3 +45,38 @@ def compare_batch(batch, oracles, avail_replicas=(0,), time_rtol=1e-12, integ_rt
     for r in avail_replicas:
         if r < R:
             assert np.array_equal(batch.avail_sites(r), oracles[r].avail_sites), "avail_sites differ (replica %d)" % r
+
+
+def oracle_checkpoints(blob, size, seeds, rates, chunks, workers, timeout=600):
+    """Oracle trajectories of len(seeds) replicas on `workers` host processes (tests/oracle_worker.py started
+    with subprocess: independent of this process' CUDA context, bounded by `timeout` seconds).
+    -> (lattice[R][C][V] int8, procstat[R][C][P], kmc_time[R][C], kmc_step[R][C], status[R][C])."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    R = len(seeds)
+    workers = max(1, min(int(workers), R))
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = []
+        for w in range(workers):
+            ids = np.arange(w, R, workers)
+            fin, fout = os.path.join(tmp, "in%d.npz" % w), os.path.join(tmp, "out%d.npz" % w)
+            np.savez(fin, blob=blob, size=np.asarray(size), seeds=np.asarray(seeds)[ids], ids=ids,
+                     rates=np.asarray(rates)[ids], chunks=np.asarray(chunks))
+            procs.append((ids, fout, subprocess.Popen([sys.executable, os.path.join(here, "oracle_worker.py"), fin, fout])))
+        out = None
+        for ids, fout, p in procs:
+            try:
+                rc = p.wait(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                raise
+            assert rc == 0, "oracle worker failed"
+            d = np.load(fout)
+            if out is None:
+                out = [np.zeros((R,) + d[k].shape[1:], d[k].dtype) for k in ("lattice", "procstat", "time", "step", "status")]
+            for a, k in zip(out, ("lattice", "procstat", "time", "step", "status")):
+                a[ids] = d[k]
+    return out
