@@ -80,6 +80,8 @@ def lib():
         "kmos_b200_set_configuration": (C.c_int, [vp, i32, arr(np.int32), i32]),
         "kmos_b200_do_kmc_steps": (C.c_int, [vp, i64]),
         "kmos_b200_synchronize": (C.c_int, [vp]),
+        "kmos_b200_reload_replica": (C.c_int, [vp, i32, arr(np.int32), arr(np.int32), arr(np.int32), arr(np.int64),
+                                               arr(np.float64), f64, i64]),
         "kmos_b200_get_next_kmc_step": (C.c_int, [vp, arr(np.int32), arr(np.int32)]),
         "kmos_b200_run_proc_nr": (C.c_int, [vp, arr(np.int32), arr(np.int32)]),
         "kmos_b200_timer_start": (C.c_int, [vp]),
@@ -124,6 +126,7 @@ EXPORTED = [
     "kmos_b200_get_avail_sites", "kmos_b200_get_status", "kmos_b200_get_error_info", "kmos_b200_tally_words",
     "kmos_b200_reduce_tallies", "kmos_b200_philox_next", "kmos_b200_batch_set_stream",
     "kmos_b200_measure_smem_bandwidth", "kmos_b200_get_next_kmc_step", "kmos_b200_run_proc_nr",
+    "kmos_b200_reload_replica",
 ]
 
 

@@ -1033,6 +1033,58 @@ extern "C" int kmos_b200_get_avail_sites(kmos_b200_batch* b, int32_t replica, in
     return KMOS_B200_OK;
 }
 
+// base.reload_system for one replica (base.mpy:365-510): every array of the reference's .reload file, written
+// verbatim -- in particular avail_sites keeps the stored ORDER (a touch-up would rebuild it in lattice order
+// and change the trajectory).  The two planes must describe the same lists; otherwise KMOS_B200_ERR_ARG.
+extern "C" int kmos_b200_reload_replica(kmos_b200_batch* b, int32_t replica, const int32_t* species,
+                                        const int32_t* avail, const int32_t* nr_of_sites, const int64_t* procstat,
+                                        const double* integ_rates, double kmc_time, int64_t kmc_step) {
+    if (!species || !avail || !nr_of_sites || !procstat || replica < 0 || replica >= b->R)
+        return set_err(KMOS_B200_ERR_ARG, "reload_replica: bad argument");
+    const KbModelView& m = b->model->h;
+    if (m.backend == KB_BACKEND_OTF) return set_err(KMOS_B200_ERR_UNSUPPORTED, "reload_replica: otf keeps rates_matrix, not supported");
+    const int P = m.n_proc, C = b->g.ncells, V = b->g.volume, sp = m.spuck;
+    std::vector<uint8_t> lat(b->lat_stride, KB_NULL_SPECIES);
+    for (int i = 0; i < V; ++i) {
+        if (species[i] >= m.n_species) return set_err(KMOS_B200_ERR_ARG, "reload_replica: species id out of range");
+        lat[i] = species[i] < 0 ? KB_NULL_SPECIES : (uint8_t)species[i];
+    }
+    std::vector<unsigned char> h1(b->plane_bytes, 0), h2(b->plane_bytes, 0);
+    auto put = [&](std::vector<unsigned char>& h, size_t i, int v) {
+        if (b->idx32) ((uint32_t*)h.data())[i] = (uint32_t)v; else ((uint16_t*)h.data())[i] = (uint16_t)v;
+    };
+    for (int q = 0; q < P; ++q) {
+        const int n = m.procsite[q], nq = nr_of_sites[q];
+        if (nq < 0 || nq > C) return set_err(KMOS_B200_ERR_ARG, "reload_replica: nr_of_sites out of range");
+        for (int k = 0; k < nq; ++k) {
+            const int site = avail[((size_t)q * V + k) * 2];  // avail_sites(q, k, 1), 1-based site number
+            if (site < 1 || site > V || (site - 1) % sp + 1 != n || avail[((size_t)q * V + site - 1) * 2 + 1] != k + 1)
+                return set_err(KMOS_B200_ERR_ARG, "reload_replica: avail_sites planes are inconsistent");
+            put(h1, (size_t)q * C + k, (site - 1) / sp);
+            put(h2, (size_t)q * C + (site - 1) / sp, k + 1);
+        }
+        int back = 0;
+        for (int i = 0; i < V; ++i) back += avail[((size_t)q * V + i) * 2 + 1] != 0;
+        if (back != nq) return set_err(KMOS_B200_ERR_ARG, "reload_replica: avail_sites planes are inconsistent");
+    }
+    int rc = ensure_canonical(b);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(b->stream));
+    std::vector<double> zeros(P, 0.0);
+    CU(cudaMemcpy(b->lattice + (size_t)replica * b->lat_stride, lat.data(), lat.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy((char*)b->p1 + (size_t)replica * b->plane_bytes, h1.data(), b->plane_bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy((char*)b->p2 + (size_t)replica * b->plane_bytes, h2.data(), b->plane_bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b->nsites + (size_t)replica * P, nr_of_sites, (size_t)P * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b->procstat + (size_t)replica * P, procstat, (size_t)P * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b->integ + (size_t)replica * P, integ_rates ? integ_rates : zeros.data(), (size_t)P * 8, cudaMemcpyHostToDevice));
+    KbScalars sc;
+    CU(cudaMemcpy(&sc, b->sc + replica, sizeof sc, cudaMemcpyDeviceToHost));
+    sc.kmc_time = kmc_time; sc.kmc_step = kmc_step; sc.kmc_time_step = 0.0; sc.status = KB_OK;
+    for (int i = 0; i < 5; ++i) sc.err[i] = 0;
+    CU(cudaMemcpy(b->sc + replica, &sc, sizeof sc, cudaMemcpyHostToDevice));
+    return launch_generic(b, KB_MODE_ACCUM, 0, 0, replica);
+}
+
 extern "C" int kmos_b200_tally_words(const kmos_b200_batch* b) {
     const KbModelView& m = b->model->h;
     return 2 * m.n_proc + m.n_species * m.spuck + 3;

@@ -141,6 +141,29 @@ class Batch(object):
         site = np.ascontiguousarray(np.broadcast_to(np.asarray(site, np.int32), (self.R,)))
         capi.check(self.L.kmos_b200_run_proc_nr(self.h, proc, site))
 
+    # ---- restart files (base.save_system / base.reload_system) -----------------------------------------
+    def save_system(self, path, replica=0):
+        """Write replica `replica` as a reference-format .reload file (kmos_b200/checkpoint.py)."""
+        from . import checkpoint
+        r = int(replica)
+        state = dict(kmc_time=self.kmc_time[r], kmc_step=self.kmc_step[r], procstat=self.procstat[r],
+                     nr_of_sites=self.nr_of_sites[r], rates=self.rates[r], integ_rates=self.integ_rates[r],
+                     lattice=self.lattice[r], avail_sites=self.avail_sites(r))
+        checkpoint.write_reload(path, state)
+
+    def reload_system(self, path, replica=0):
+        """Restore replica `replica` from a .reload file; stepping continues bit-identically (same Philox key)."""
+        from . import checkpoint
+        st = checkpoint.read_reload(path)
+        if st["nr_of_proc"] != self.P or st["volume"] != self.volume:
+            raise ValueError("reload file is for nr_of_proc=%d volume=%d" % (st["nr_of_proc"], st["volume"]))
+        integ = np.ascontiguousarray(st.get("integ_rates", np.zeros(self.P)), dtype=np.float64)
+        capi.check(self.L.kmos_b200_reload_replica(
+            self.h, int(replica), np.ascontiguousarray(st["lattice"], np.int32),
+            np.ascontiguousarray(st["avail_sites"], np.int32).reshape(-1),
+            np.ascontiguousarray(st["nr_of_sites"], np.int32), np.ascontiguousarray(st["procstat"], np.int64),
+            integ, float(st["kmc_time"]), int(st["kmc_step"])))
+
     def set_stream(self, cuda_stream):
         """Run on a caller-owned CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
         capi.check(self.L.kmos_b200_batch_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
