@@ -141,6 +141,11 @@ class Batch(object):
         site = np.ascontiguousarray(np.broadcast_to(np.asarray(site, np.int32), (self.R,)))
         capi.check(self.L.kmos_b200_run_proc_nr(self.h, proc, site))
 
+    def set_kmc_time(self, t):
+        """base.set_kmc_time for every replica: t[R] (a scalar is broadcast)."""
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.float64), (self.R,)))
+        capi.check(self.L.kmos_b200_set_kmc_time(self.h, t))
+
     # ---- restart files (base.save_system / base.reload_system) -----------------------------------------
     def save_system(self, path, replica=0):
         """Write replica `replica` as a reference-format .reload file (kmos_b200/checkpoint.py)."""

@@ -285,6 +285,9 @@ class KMC_Model(object):
             get_accum_rate=lambda i: float(b.accum_rates[0, i - 1]),
             set_rate_const=lambda i, r: b.set_rate_const(i, r, replica=0),
             get_avail_site=lambda proc, field, switch: int(b.avail_sites(0)[proc - 1, field - 1, switch - 1]),
+            set_kmc_time=lambda t: b.set_kmc_time(np.where(np.arange(b.R) == 0, float(t), b.kmc_time)),
+            save_system=lambda: b.save_system("%s.reload" % self.ir.get("fixture", "kmc_model"), 0),
+            reload_system=lambda: b.reload_system("%s.reload" % self.ir.get("fixture", "kmc_model"), 0),
             update_accum_rate=lambda: None, is_allocated=lambda: True, null_species=-1,
             get_null_species=lambda: -1, get_volume=lambda: b.volume)
         self.lattice = _Namespace(
@@ -294,6 +297,10 @@ class KMC_Model(object):
                                                                      site[2] % self.size[2], site[3] - 1]),
             calculate_lattice2nr=lambda site: int(self.model.spuck * ((site[0] % self.size[0]) + self.size[0] * (
                 (site[1] % self.size[1]) + self.size[1] * (site[2] % self.size[2]))) + site[3]),
+            calculate_nr2lattice=lambda nr: [((nr - 1) // self.model.spuck) % self.size[0],
+                                             ((nr - 1) // self.model.spuck) // self.size[0] % self.size[1],
+                                             ((nr - 1) // self.model.spuck) // (self.size[0] * self.size[1]),
+                                             (nr - 1) % self.model.spuck + 1],
             deallocate_system=self.deallocate)
         self.proclist = _Namespace(
             do_kmc_steps=self.do_steps, do_kmc_step=lambda: self.do_steps(1), nr_of_proc=self.model.n_proc,
