@@ -63,6 +63,7 @@ struct KbModelView {
     const int32_t* blob;
     int backend, n_species, n_proc, spuck, dim, default_species, n_layers, default_layer, n_routines, n_gr,
         lut_total;
+    int null_species;  // id the model passes to base.set_null_species (multi-lattice models), else -1
     const int32_t *routines, *code, *runproc, *init, *gr, *procsite, *dev, *dev_hbm;
     int dev_len, dev_hbm_len;
 };
@@ -163,7 +164,7 @@ static inline bool kb_model_view(const int32_t* hblob, int64_t n_words, const in
     if (n_words < 14 || hblob[0] != KB20_MAGIC || hblob[1] != KB20_VERSION) return false;
     m->blob = base;
     m->backend = hblob[2]; m->n_species = hblob[3]; m->n_proc = hblob[4]; m->spuck = hblob[5]; m->dim = hblob[6];
-    m->default_species = hblob[7]; m->n_layers = hblob[8]; m->default_layer = hblob[9]; m->n_routines = hblob[10];
+    m->default_species = hblob[7] & 0xFFFF; m->null_species = (hblob[7] >> 16) - 1; m->n_layers = hblob[8]; m->default_layer = hblob[9]; m->n_routines = hblob[10];
     m->n_gr = hblob[11]; m->lut_total = hblob[12];
     int len;
     const int32_t* p;

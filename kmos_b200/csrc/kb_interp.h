@@ -371,7 +371,8 @@ struct KbInterp {
 
     // initialize_state: default species everywhere, then touchup cell by cell (z, y, x-fastest order)
     KB_HDN void init_state(int layer) {
-        for (int i = 0; i < g.volume; ++i) r.lattice[i] = KB_NULL_SPECIES;
+        const uint8_t null_fill = m.null_species < 0 ? (uint8_t)KB_NULL_SPECIES : (uint8_t)m.null_species;
+        for (int i = 0; i < g.volume; ++i) r.lattice[i] = null_fill;
         for (int q = 0; q < m.n_proc; ++q) {
             r.nsites[q] = 0; r.integ[q] = 0.0; r.accum[q] = 0.0; r.procstat[q] = 0;
         }

@@ -337,8 +337,10 @@ class _BlockParser(object):
                         _ratex(args[2], env, variables)]
             if lname == "increment_procstat":
                 return None
-            if lname in ("create", "annihilate") or lname.startswith(("create_", "annihilate_")):
-                raise FortranIRError("multi-lattice create/annihilate is not supported yet (%s)" % name)
+            if lname.startswith(("create_", "annihilate_")) and len(args) == 2:
+                # multi-lattice models (kmos/io/__init__.py:2445-2560): create_<site>(site, species) /
+                # annihilate_<site>(site, species) -- one instance per species actually passed
+                return ["call", "%s@%d" % (name, env.species_id(args[1])), _coord(args[0], env, variables)]
             return ["call", name, _coord(args[0], env, variables)]
         m = re.match(r"^call\s+(\w+)\s*$", ln, re.I)
         if m:
@@ -440,6 +442,7 @@ def _read(path):
 
 def _site_of_routine(name, env):
     """`put_co_ruo2_bridge` -> site index of `ruo2_bridge` (longest matching suffix)."""
+    name = name.partition("@")[0]
     best = None
     for sname, idx in env.sites.items():
         if name.lower().endswith("_" + sname.lower()):
@@ -523,6 +526,9 @@ def parse_export_dir(path, backend=None):
         "spuck": spuck,
         "species": sorted(env.species, key=lambda n: env.species[n]),
         "default_species": env.misc["default_species"],
+        # multi-lattice models declare a species called null_species and hand it to base.set_null_species
+        # (proclist_generic_subroutines.mpy:223): sites outside the initial layer hold this id, not -1
+        "null_species": next((v for k, v in env.species.items() if k.lower() == "null_species"), -1),
         "layers": sorted(env.layers, key=lambda n: env.layers[n]),
         "default_layer": env.misc["default_layer"],
         "sites": site_names,
@@ -549,11 +555,22 @@ def parse_export_dir(path, backend=None):
     def need(name):
         if name in ir["routines"]:
             return
-        src = routines.get(name) or extra.get(name)
+        base, _, sp = name.partition("@")
+        src = routines.get(base) or extra.get(base)
         if src is None:
-            raise FortranIRError("routine %r not found" % name)
+            raise FortranIRError("routine %r not found" % base)
         argname = src[1][0] if src[1] else "site"
-        stmts = _parse_routine(src[2], env, {argname: [0, 0, 0, 0]})
+        if sp:  # create_/annihilate_ instance: bind the routine's species argument to the constant passed
+            spname = src[1][1] if len(src[1]) > 1 else "species"
+            if spname in env.species:
+                raise FortranIRError("species argument %r shadows a species constant" % spname)
+            env.species[spname] = int(sp)
+            try:
+                stmts = _parse_routine(src[2], env, {argname: [0, 0, 0, 0]})
+            finally:
+                del env.species[spname]
+        else:
+            stmts = _parse_routine(src[2], env, {argname: [0, 0, 0, 0]})
         ir["routines"][name] = stmts
         for callee in _callees(stmts):
             need(callee)
@@ -632,9 +649,10 @@ def _parse_run_proc_nr(body, env, nr_of_proc):
         m = re.match(r"^call\s+(\w+)\s*\((.*)\)\s*$", ln, re.I)
         if m and cur is not None:
             args = _split_top(m.group(2))
-            if m.group(1).lower().startswith(("create_", "annihilate_")):
-                raise FortranIRError("multi-lattice create/annihilate is not supported yet")
-            calls[cur[0]].append(["call", m.group(1), _coord(args[0], env, variables)])
+            cname = m.group(1)
+            if cname.lower().startswith(("create_", "annihilate_")) and len(args) == 2:
+                cname = "%s@%d" % (cname, env.species_id(args[1]))
+            calls[cur[0]].append(["call", cname, _coord(args[0], env, variables)])
             continue
         if cur is None:
             continue

@@ -4,7 +4,7 @@ The blob is what crosses the C-ABI (`kmos_b200_model_create`, include/kmos_b200.
 oracle loads.  It is a flat little-endian int32 array:
 
     [0]  magic 0x4B423230 ("KB20")     [1] version          [2] backend (0 local_smart,1 lat_int,2 otf)
-    [3]  n_species   [4] n_proc   [5] spuck   [6] model_dimension   [7] default_species
+    [3]  n_species   [4] n_proc   [5] spuck   [6] model_dimension   [7] default_species | (null_species id + 1) << 16
     [8]  n_layers    [9] default_layer   [10] n_routines   [11] n_gr   [12] lut_total
     [13] n_sections  then n_sections x (id, offset_words, length_words)
 
@@ -218,7 +218,7 @@ def build_blob(ir, with_device=True):
         if lay is None:
             init += [-1, -1]
             continue
-        defaults = [["replace", [0, 0, 0, n], -1, sp] for n, sp in lay["defaults"]]
+        defaults = [["replace", [0, 0, 0, n], ir.get("null_species", -1), sp] for n, sp in lay["defaults"]]
         touch = [["call", r, off] for r, off in lay["touchups"]]
         init += [asm.anon_routine("__init_defaults_%d" % layer, defaults),
                  asm.anon_routine("__init_touchup_%d" % layer, touch)]
@@ -273,7 +273,8 @@ def build_blob(ir, with_device=True):
             info["device_hbm"] = hbm_info
 
     header = [MAGIC, VERSION, BACKENDS[ir["backend"]], len(ir["species"]), nproc, ir["spuck"],
-              ir["model_dimension"], ir["default_species"], nlayers, ir["default_layer"],
+              ir["model_dimension"], ir["default_species"] | ((ir.get("null_species", -1) + 1) << 16), nlayers,
+              ir["default_layer"],
               len(asm.routine_code), len(asm.gr_ids), lut_total, len(sections)]
     dir_len = 3 * len(sections)
     off = len(header) + dir_len

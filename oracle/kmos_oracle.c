@@ -47,6 +47,7 @@ typedef struct {
     int32_t *blob;
     int backend, n_species, n_proc, spuck, dim, default_species, n_layers, default_layer, n_routines, n_gr,
         lut_total;
+    int null_species; /* id handed to base.set_null_species by multi-lattice models, else -1 */
     const int32_t *routines, *code, *runproc, *init, *gr;
     /* system (base.mpy:85-205) */
     int size[3];
@@ -483,7 +484,7 @@ oracle_t *kmos_oracle_create(const int32_t *blob, int64_t n_words, const int32_t
     memcpy(o->blob, blob, (size_t)n_words * 4);
     const int32_t *b = o->blob;
     o->backend = b[2]; o->n_species = b[3]; o->n_proc = b[4]; o->spuck = b[5]; o->dim = b[6];
-    o->default_species = b[7]; o->n_layers = b[8]; o->default_layer = b[9]; o->n_routines = b[10];
+    o->default_species = b[7] & 0xFFFF; o->null_species = (b[7] >> 16) - 1; o->n_layers = b[8]; o->default_layer = b[9]; o->n_routines = b[10];
     o->n_gr = b[11]; o->lut_total = b[12];
     int len;
     o->routines = find_section(b, SEC_ROUTINES, &len);
@@ -495,7 +496,7 @@ oracle_t *kmos_oracle_create(const int32_t *blob, int64_t n_words, const int32_t
     o->volume = o->size[0] * o->size[1] * o->size[2] * o->spuck;
     size_t V = (size_t)o->volume, P = (size_t)o->n_proc;
     o->lattice = (int32_t *)malloc(V * 4);
-    for (size_t i = 0; i < V; ++i) o->lattice[i] = -1; /* null_species */
+    for (size_t i = 0; i < V; ++i) o->lattice[i] = o->null_species; /* base.allocate_system: lattice = null_species */
     o->avail1 = (int32_t *)calloc(P * V, 4);
     o->avail2 = (int32_t *)calloc(P * V, 4);
     o->nr_of_sites = (int32_t *)calloc(P, 4);
@@ -539,7 +540,7 @@ static void touchup_all(oracle_t *o, int layer) {
 int kmos_oracle_init_state(oracle_t *o, int layer) {
     if (layer < 0 || layer >= o->n_layers || o->init[2 * layer] < 0) return ORACLE_BAD_MODEL;
     size_t V = (size_t)o->volume, P = (size_t)o->n_proc;
-    for (size_t i = 0; i < V; ++i) o->lattice[i] = -1;
+    for (size_t i = 0; i < V; ++i) o->lattice[i] = o->null_species;
     memset(o->avail1, 0, P * V * 4); memset(o->avail2, 0, P * V * 4); memset(o->nr_of_sites, 0, P * 4);
     memset(o->integ_rates, 0, P * 8); memset(o->accum_rates, 0, P * 8); memset(o->procstat, 0, P * 8);
     if (o->rates_matrix) memset(o->rates_matrix, 0, P * (V + 1) * 8);

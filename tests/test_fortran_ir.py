@@ -75,8 +75,21 @@ def test_parses_reference_golden_exports(dirname, backend, nproc):
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "tests", "export_test")), reason="reference checkout absent")
-def test_multilattice_export_is_rejected_loudly():
-    """Pd/PdO uses create_/annihilate_ routines (kmos/io/__init__.py:2445-2560): not supported yet."""
-    path = os.path.join(REF, "tests", "export_test", "reference_pdopd_local_smart")
-    with pytest.raises(fortran_ir.FortranIRError):
-        fortran_ir.parse_export_dir(path, "local_smart")
+@pytest.mark.parametrize("dirname,backend", [("reference_pdopd_local_smart", "local_smart"),
+                                             ("reference_pdopd_lat_int", "lat_int")])
+def test_parses_multilattice_exports(dirname, backend):
+    """Pd/PdO: create_<site>(site, species) / annihilate_<site>(site, species) (kmos/io/__init__.py:2445-2560)
+    become one routine instance per species passed; the declared null_species is what fills absent sites."""
+    ir = fortran_ir.parse_export_dir(os.path.join(REF, "tests", "export_test", dirname), backend)
+    assert len(ir["procs"]) == 46 and ir["spuck"] == 25 and len(ir["layers"]) == 2
+    assert ir["null_species"] == ir["species"].index("null_species") == 4
+    if backend == "local_smart":
+        inst = [n for n in ir["routines"] if "@" in n]
+        assert any(n.startswith("create_") for n in inst) and any(n.startswith("annihilate_") for n in inst)
+        st = ir["routines"]["create_Pd100_h1@2"][0]
+        assert st[0] == "replace" and st[2:] == [4, 2]  # replace_species(site, null_species, species)
+    blob, info = tables.build_blob(ir)
+    assert blob[4] == 46 and (blob[7] >> 16) - 1 == 4
+    committed = tables.load_ir(os.path.join(os.path.dirname(__file__), "golden", "models",
+                                            "pdopd_%s.json" % backend))
+    assert committed["routines"] == ir["routines"] and committed["run_proc"] == ir["run_proc"]

@@ -48,7 +48,31 @@ def test_local_smart_parity(name, size, R, chunks, kernel):
     batch.close()
 
 
+@pytest.mark.parametrize("kernel", ["generic", "warp_hbm"])
+def test_multilattice_pdopd_local_smart_parity(kernel):
+    """Pd(100)/PdO model of the reference's export tests (two lattices, 25 sites per cell, create_/annihilate_
+    routines, a declared null_species): too many sites per cell for the lane tables, so the shared-memory
+    kernel declines and the two HBM-state kernels must match the oracle."""
+    engine = _engine()
+    ir, blob, info = load_model("pdopd_local_smart")
+    R, size, chunks = 6, [6, 5], [3000, 3000]
+    rates, lut, seeds = make_inputs(ir, info, R, seed=11)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    auto = engine.Batch(model, R, size, seeds=seeds, rates=rates)
+    assert auto.kernel_info()["kernel_name"] == "warp_hbm"
+    auto.close()
+    kind = capi.KERNEL_WARP_HBM if kernel == "warp_hbm" else capi.KERNEL_GENERIC
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=kind)
+    gen = run_oracles(blob, size, rates, lut, seeds, chunks)
+    compare_batch(batch, next(gen), avail_replicas=(0,))
+    for n, oracles in zip(chunks, gen):
+        batch.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(0, R - 1))
+    batch.close()
+
+
 LATINT_CASES = [
+    ("pdopd_lat_int", [6, 5], 5, [3000, 3000]),
     ("ab_lat_int", [10, 12], 6, [1500, 1500]),
     ("mini_101_lat_int", [7, 5], 5, [700, 700]),
     ("zgb_lat_int", [12, 12], 5, [2000, 2000]),

@@ -50,6 +50,8 @@ CASES = [
     ("pairwise_lat_int", [12, 12], 3000),
     ("pairwise_local_smart", [8, 9], 2000),
     ("pairwise_otf_otf", [12, 10], 3000),
+    ("pdopd_local_smart", [6, 5], 4000),  # multi-lattice: create_/annihilate_ routines, null_species = 4
+    ("pdopd_lat_int", [6, 5], 4000),
 ]
 
 

@@ -216,6 +216,25 @@ def copy_reference_goldens():
     print("wrote %s %s" % (out, arrays[0].shape))
 
 
+# Fortran the reference itself keeps under version control (byte-golden exports of its own tests): parsed as is.
+GOLDEN_EXPORTS = [
+    ("pdopd", "local_smart", "tests/export_test/reference_pdopd_local_smart"),
+    ("pdopd", "lat_int", "tests/export_test/reference_pdopd_lat_int"),
+]
+
+
+def golden_export_fixtures(outdir):
+    for name, backend, rel in GOLDEN_EXPORTS:
+        ir = fortran_ir.parse_export_dir(os.path.join(REF, rel), backend)
+        ir["fixture"] = {"model": name, "backend": backend, "settings_written": False,
+                         "generator": "%s (reference, committed Fortran) -> kmos_b200.fortran_ir" % rel}
+        ir.update({"parameters": {}, "process_defs": []})
+        out = os.path.join(outdir, "%s_%s.json" % (name, backend))
+        with open(out, "w") as f:
+            json.dump(ir, f, separators=(",", ":"), sort_keys=True)
+        print("wrote %s (%d procs, %d bytes)" % (out, len(ir["procs"]), os.path.getsize(out)))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--keep-fortran", default=None, help="directory to keep the generated Fortran in")
@@ -226,6 +245,10 @@ def main():
     os.makedirs(outdir, exist_ok=True)
     if not args.only:
         copy_reference_goldens()
+    if not args.only or args.only == "pdopd":
+        golden_export_fixtures(outdir)
+    if args.only == "pdopd":
+        return
     for name, builder, backends in MODELS:
         if args.only and args.only != name:
             continue
