@@ -390,8 +390,8 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
     const double rate1 = has1 ? prm.rates[(size_t)rep * P + q1] : 0.0;
     double integ0 = has0 ? prm.integ[(size_t)rep * P + q0] : 0.0;
     double integ1 = has1 ? prm.integ[(size_t)rep * P + q1] : 0.0;
-    long long ps0 = has0 ? prm.procstat[(size_t)rep * P + q0] : 0;
-    long long ps1 = has1 ? prm.procstat[(size_t)rep * P + q1] : 0;
+    const long long ps0 = has0 ? prm.procstat[(size_t)rep * P + q0] : 0;
+    const long long ps1 = has1 ? prm.procstat[(size_t)rep * P + q1] : 0;
 
     KbScalars* const scp = prm.sc + rep;  // only the fields that change are kept in registers / written back
     double kmc_time = scp->kmc_time, kmc_dt = scp->kmc_time_step;
@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
     __syncwarp();
     const int lastp = P - 1;
 
+    uint32_t cnt0 = 0, cnt1 = 0;      // events of this lane's processes in this item (< 2^32 steps per item)
     double rng_a = 0.0, rng_b = 0.0;  // even lanes: (-log(ran_time), ran_proc); odd lanes: (ran_site, -)
 
     for (long long it = 0; it < my_steps && status == KB_OK; ++it) {
@@ -482,12 +483,11 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
         k = min(k, nsel);
         const uint32_t spi = procinfo[pidx];
         const int cell = kb_p1_get<SPLIT>(p1, p1hi, kb_slot((int)(spi & 63u), (int)((spi >> 6) & 1u), cap, k - 1));
-        if ((pidx & 31) == lane) {
-            if (PPL == 2 && pidx >= 32) ps1 += 1; else ps0 += 1;
-        }
+        cnt0 += (pidx == lane);
+        if (PPL == 2) cnt1 += (pidx == lane + 32);
 
         // -- run_proc_nr(pidx+1, site): lattice writes, then rounds of list operations
-        const uint4 eh = events[2 * pidx], ew = events[2 * pidx + 1];
+        const uint4 eh = events[2 * pidx];
         const int ops_start = (int)(eh.x & 0xFFFFu), n_rounds = (int)((eh.x >> 16) & 15u), n_writes = (int)((eh.x >> 20) & 15u);
         int nb;  // lane l: cell index of neighbour offset l
         if (NBT) {
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
             nb = cc.cell_at(my_off);
         }
         {
-            const uint32_t w = lane == 0 ? ew.x : (lane == 1 ? ew.y : (lane == 2 ? ew.z : ew.w));
+            const uint32_t w = reinterpret_cast<const uint32_t*>(events + 2 * pidx + 1)[lane & 3];  // lane < 4: its write
             const int wcell = __shfl_sync(KB_FULL, nb, (int)(w & 31u));
             if (lane < n_writes) {
                 const int idx = wcell * spuck + (int)((w >> 5) & 7u) - 1;
@@ -627,8 +627,8 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
         for (int i = lane; i < prm.lat_stride / 16; i += 32) sl[i] = dl[i];
     }
     for (int i = lane; i < P; i += 32) g_ns[i] = nS[i];
-    if (has0) { prm.integ[(size_t)rep * P + q0] = integ0; prm.procstat[(size_t)rep * P + q0] = ps0; }
-    if (has1) { prm.integ[(size_t)rep * P + q1] = integ1; prm.procstat[(size_t)rep * P + q1] = ps1; }
+    if (has0) { prm.integ[(size_t)rep * P + q0] = integ0; prm.procstat[(size_t)rep * P + q0] = ps0 + cnt0; }
+    if (has1) { prm.integ[(size_t)rep * P + q1] = integ1; prm.procstat[(size_t)rep * P + q1] = ps1 + cnt1; }
     if (lane == 0) {
         scp->kmc_time = kmc_time; scp->kmc_time_step = kmc_dt; scp->kmc_step = kmc_step; scp->status = status;
     }

@@ -918,6 +918,8 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     }
     const char* ep_env = getenv("KMOS_B200_EPOCHS");
     if (ep_env && atoi(ep_env) > 0) epochs = atoi(ep_env);
+    // the kernel counts an item's events per process in 32 bits
+    if ((n + epochs - 1) / epochs > 0x40000000LL) epochs = (n + 0x3fffffffLL) / 0x40000000LL;
     sp.chunk = (n + epochs - 1) / epochs;
     epochs = (n + sp.chunk - 1) / sp.chunk;
     if (epochs * (long long)b->R > 0x7fffffffLL) return set_err(KMOS_B200_ERR_ARG, "do_kmc_steps: too many work items");
