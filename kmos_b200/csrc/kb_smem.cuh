@@ -412,11 +412,14 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
     uint32_t cnt0 = 0, cnt1 = 0;      // events of this lane's processes in this item (< 2^32 steps per item)
     double rng_a = 0.0, rng_b = 0.0;  // even lanes: (-log(ran_time), ran_proc); odd lanes: (ran_site, -)
 
-    for (long long it = 0; it < my_steps && status == KB_OK; ++it) {
-        const int sub = (int)(it & (KB_RNG_BATCH - 1));
+    const long long step0 = kmc_step;  // kmc_step = step0 + it inside the loop (items are < 2^30 steps)
+    const int n_it = (int)my_steps;
+    int it = 0;
+    for (; it < n_it && status == KB_OK; ++it) {
+        const int sub = it & (KB_RNG_BATCH - 1);
         if (sub == 0) {
             // 16 steps of uniforms at once: lane l serves step kmc_step + l/2, Philox slot l&1
-            const unsigned long long st = (unsigned long long)kmc_step + (unsigned)(lane >> 1);
+            const unsigned long long st = (unsigned long long)(step0 + it) + (unsigned)(lane >> 1);
             uint32_t rnd[4];
             kb_philox4x32_10((uint32_t)st, (uint32_t)(st >> 32), replica_id, (uint32_t)(lane & 1), k0, k1, rnd);
             const double u0 = (double)(((((uint64_t)rnd[1] << 32) | rnd[0]) >> 11) + (uint64_t)((lane & 1) ^ 1)) * 0x1.0p-53;
@@ -461,7 +464,6 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
         // -- update_clocks / update_integ_rate
         kmc_dt = neg_log_u / total;
         kmc_time = __dadd_rn(kmc_time, kmc_dt);
-        kmc_step += 1;
         integ0 = __dadd_rn(integ0, __dmul_rn(pr0, kmc_dt));
         if (PPL == 2) integ1 = __dadd_rn(integ1, __dmul_rn(pr1, kmc_dt));
 
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
             pidx = P - (__popc(ge0) + __popc(ge1));
         }
         const int nsel = __shfl_sync(KB_FULL, (PPL == 2 && pidx >= 32) ? n1 : n0, pidx & 31);
-        if (nsel <= 0) { status = KB_DEADLOCK; break; }
+        if (nsel <= 0) { status = KB_DEADLOCK; ++it; break; }  // the clock has advanced: the step counts
         int k = (int)__dadd_rn(1.0, __dmul_rn(ran_site, (double)nsel));
         k = min(k, nsel);
         const uint32_t spi = procinfo[pidx];
@@ -599,13 +601,14 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
                 if (lane == 0) {
                     const int idx = wcell * spuck + (int)((w >> 5) & 7u) - 1;
                     scp->err[0] = (int)((w >> 8) & 15u); scp->err[1] = (int)((w >> 12) & 15u);
-                    scp->err[2] = lat[idx]; scp->err[3] = idx + 1; scp->err[4] = (int)kmc_step;
+                    scp->err[2] = lat[idx]; scp->err[3] = idx + 1; scp->err[4] = (int)(step0 + it + 1);
                 }
             }
             status = __reduce_max_sync(KB_FULL, status);
         }
     }
     status = __reduce_max_sync(KB_FULL, status);
+    kmc_step = step0 + it;
 
     // ---- write back -----------------------------------------------------------------------------------
     __syncwarp();
