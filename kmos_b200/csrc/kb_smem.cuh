@@ -511,11 +511,12 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
                 }
             }
         }
-        const unsigned long long ends = ((unsigned long long)eh.z << 32) | eh.y;
+        // cumulative op counts of the rounds, one byte each; bytes past the last round repeat the total
+        unsigned long long ends = ((unsigned long long)eh.z << 32) | eh.y;
         // Software pipeline over the rounds: the op words of round r+1 (read-only tables) and the cells they
         // name are fetched while round r's list updates are in flight; only nr_of_sites, the class entries
         // and the lists themselves have to wait for the __syncwarp between rounds.
-        int endr = n_rounds > 0 ? (int)(ends & 255u) : 0;
+        int endr = (int)((uint32_t)ends & 255u);
         bool valid = lane < endr;
         const uint32_t* op = ops + (ops_start + lane) * STRIDE;
         uint32_t h = valid ? op[0] : 0u, h1 = valid ? op[1] : 0u;
@@ -525,9 +526,9 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
         int ca = __shfl_sync(KB_FULL, nb, (int)((h >> 4) & 31u));
         for (int r = 0; r < n_rounds; ++r) {
             // -- fetch round r+1
-            const bool more = r + 1 < n_rounds;
-            const int end_n = more ? (int)((ends >> (8 * (r + 1))) & 255u) : endr;
-            const bool valid_n = more && endr + lane < end_n;
+            ends >>= 8;
+            const int end_n = (int)((uint32_t)ends & 255u);
+            const bool valid_n = endr + lane < end_n;  // empty after the last round (same total, or 0)
             const uint32_t* op_n = ops + (ops_start + endr + lane) * STRIDE;
             const uint32_t h_n = valid_n ? op_n[0] : 0u, h1_n = valid_n ? op_n[1] : 0u;
             uint32_t cw_n[NCOND > 0 ? NCOND : 1];
