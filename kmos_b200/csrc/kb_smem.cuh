@@ -278,7 +278,7 @@ struct KbCellCtx {
 
 // PPL: processes per lane (1: P <= 32, 2: P <= 64);  NCOND: largest number of dynamic probes of an add
 // Specialised op (host: specialise_tables in kmos_b200.cu): 2 + NCOND words
-//   w0 = kind | ncond<<1 | off_id<<4 | q<<9 | member<<15 | dir<<18
+//   w0 = kind | ncond<<1 | dir<<4 | (4*q)<<8 | off_id<<16 | member<<24   (byte-aligned: one PRMT per field)
 //   w1 = class base (cls * ncells) | first slot of the list (arena*cap, or arena*cap + cap-1 if it grows down) << 16
 //   then ncond probe words off_id | n<<5 | mask<<8
 template <int PPL, int NCOND, bool SPLIT, bool P1G, bool NBT>
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
         uint32_t cw[NCOND > 0 ? NCOND : 1];
 #pragma unroll
         for (int j = 0; j < NCOND; ++j) cw[j] = (valid && j < (int)((h >> 1) & 7u)) ? op[2 + j] : 0u;
-        int ca = __shfl_sync(KB_FULL, nb, (int)((h >> 4) & 31u));
+        int ca = __shfl_sync(KB_FULL, nb, (int)__byte_perm(h, 0u, 0x4442u));
         for (int r = 0; r < n_rounds; ++r) {
             // -- fetch round r+1
             ends >>= 8;
@@ -537,15 +537,15 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
             // -- round r
             bool ok = valid;
             const int ncond = (int)((h >> 1) & 7u);
-            const int q = (int)((h >> 9) & 63u);
-            const uint32_t member = (h >> 15) & 7u;
-            const bool down = (h >> 18) & 1u;
+            int32_t* const nSq = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(nS) + __byte_perm(h, 0u, 0x4441u));
+            const uint32_t member = h >> 24;
+            const bool down = (h >> 4) & 1u;
             const int slot0 = (int)(h1 >> 16);
             uint16_t* entry = p2 + (h1 & 0xFFFFu);
             // this lane is the only one touching list q in this round: its length can be read up front, and
             // when the lists live in L2 the element a del would move is requested before the probes so that
             // the round trip overlaps them (speculative: harmless if the del does not fire)
-            const int nq = valid ? nS[q] : 0;
+            const int nq = valid ? *nSq : 0;
             int last = 0;
             if (P1G) {  // unconditional load from an always-valid slot: nothing consumes it before the del body
                 const bool want = valid && !(h & 1u) && nq > 0;
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
                     } else {
                         kb_p1_set<SPLIT>(p1, p1hi, down ? slot0 - nq : slot0 + nq, ca);
                         entry[ca] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)(nq + 1));
-                        nS[q] = nq + 1;
+                        *nSq = nq + 1;
                     }
                 } else {  // guarded del_proc (base.mpy:211-265)
                     const uint32_t e = entry[ca];
@@ -578,12 +578,12 @@ __global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemPa
                             entry[last] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)pos);
                         }
                         entry[ca] = 0;
-                        nS[q] = nq - 1;
+                        *nSq = nq - 1;
                     }
                 }
             }
             // -- rotate
-            ca = __shfl_sync(KB_FULL, nb, (int)((h_n >> 4) & 31u));
+            ca = __shfl_sync(KB_FULL, nb, (int)__byte_perm(h_n, 0u, 0x4442u));
             h = h_n; h1 = h1_n; valid = valid_n; endr = end_n;
 #pragma unroll
             for (int j = 0; j < NCOND; ++j) cw[j] = cw_n[j];

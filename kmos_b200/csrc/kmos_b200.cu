@@ -316,7 +316,7 @@ static bool specialise_tables(const int32_t* d, int ncells, int cap, std::vector
         const uint32_t p2base = cls * (uint32_t)ncells;
         const uint32_t slot0 = arena * (uint32_t)cap + (dir ? (uint32_t)cap - 1u : 0u);
         if (p2base > 0xFFFFu || slot0 > 0xFFFFu) return false;
-        o.push_back((int32_t)(kind | (ncond << 1) | (off_id << 4) | (q << 9) | (member << 15) | (dir << 18)));
+        o.push_back((int32_t)(kind | (ncond << 1) | (dir << 4) | ((4u * q) << 8) | (off_id << 16) | (member << 24)));
         o.push_back((int32_t)(p2base | (slot0 << 16)));
         for (int j = 1; j < stride; ++j) o.push_back(d[ops_off + i * stride + j]);
     }
