@@ -353,7 +353,8 @@ static void plan_latint(kmos_b200_batch* b) {
         d = m->h.dev_hbm; dlen = m->h.dev_hbm_len; b->li_mode = 1;
     }
     if (!d) return;
-    if (m->h.n_proc > 64) return;
+    if (m->h.n_proc > 256) return;
+    const int li_ppl = m->h.n_proc <= 32 ? 1 : (m->h.n_proc <= 64 ? 2 : (m->h.n_proc <= 128 ? 4 : 8));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, b->device) != cudaSuccess) return;
     // distinct offsets of one event must be distinct cells (the generated code assumes it too: folded probes,
@@ -372,9 +373,13 @@ static void plan_latint(kmos_b200_batch* b) {
     if (!magic_ok(li.magic_x, Lx, b->g.ncells) || !magic_ok(li.magic_xy, LxLy, b->g.ncells)) return;
     li.dev_words = dlen;
     li.tab_bytes = (int)align_up((size_t)li.dev_words * 4, 128);
-    li.rep_bytes = 1280;  // nr_of_sites (256 B) + two zero-prefixed product buffers (1 KB)
+    li.rep_bytes = 768 * li_ppl;  // per 32 processes: nr_of_sites, event counters (128 B each), product buffer (512 B)
     b->li_wpc = 8;
     b->li_smem_bytes = li.tab_bytes + b->li_wpc * li.rep_bytes;
+    if (li_ppl >= 4) {  // the kernels for more than 64 processes read their tables in place (kb_latint.cuh)
+        li.tab_bytes = 0;
+        b->li_smem_bytes = b->li_wpc * li.rep_bytes;
+    }
     if (b->li_smem_bytes > (int)prop.sharedMemPerBlockOptin) return;
     li.n_proc = m->h.n_proc; li.n_species = m->h.n_species; li.spuck = m->h.spuck; li.dim = m->h.dim;
     for (int a = 0; a < 3; ++a) li.size[a] = b->g.size[a];
@@ -859,16 +864,17 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         li.rates = b->rates; li.integ = b->integ; li.procstat = b->procstat; li.sc = b->sc; li.R = b->R; li.nsteps = n;
         const int threads = b->li_wpc * 32;
         void (*fn)(const KbLatintParams);
-        const bool p2l = b->model->h.n_proc > 32;
+        const int np = b->model->h.n_proc;
         const bool dense = (long long)b->R > 24LL * b->sm_count;  // more replicas than 3 CTAs/SM can hold
+        // PPL: processes per lane.  Up to 64 processes the register budget is tuned per occupancy (MINB 3/4);
+        // 65..256 processes carry 4 or 8 rate/integral/prefix registers per lane and run 2 CTAs per SM.
 #define KB_LI(PPLV, IDX, MODEV) (dense ? kb_latint_kernel<PPLV, IDX, MODEV, 4> : kb_latint_kernel<PPLV, IDX, MODEV, 3>)
-        if (b->li_mode == 0) {
-            if (p2l) fn = b->idx32 ? KB_LI(2, uint32_t, 0) : KB_LI(2, uint16_t, 0);
-            else fn = b->idx32 ? KB_LI(1, uint32_t, 0) : KB_LI(1, uint16_t, 0);
-        } else {
-            if (p2l) fn = b->idx32 ? KB_LI(2, uint32_t, 1) : KB_LI(2, uint16_t, 1);
-            else fn = b->idx32 ? KB_LI(1, uint32_t, 1) : KB_LI(1, uint16_t, 1);
-        }
+#define KB_LI_MODE(IDX, MODEV)                                               \
+        (np <= 32 ? KB_LI(1, IDX, MODEV) : np <= 64 ? KB_LI(2, IDX, MODEV)   \
+                  : np <= 128 ? kb_latint_kernel<4, IDX, MODEV, 2> : kb_latint_kernel<8, IDX, MODEV, 2>)
+        if (b->li_mode == 0) fn = b->idx32 ? KB_LI_MODE(uint32_t, 0) : KB_LI_MODE(uint16_t, 0);
+        else fn = b->idx32 ? KB_LI_MODE(uint32_t, 1) : KB_LI_MODE(uint16_t, 1);
+#undef KB_LI_MODE
 #undef KB_LI
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->li_smem_bytes));
         int per_sm = 0;
@@ -886,6 +892,7 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         }
         const char* ep_env = getenv("KMOS_B200_EPOCHS");
         if (ep_env && atoi(ep_env) > 0) epochs = atoi(ep_env);
+        if ((n + epochs - 1) / epochs > 0x40000000LL) epochs = (n + 0x3fffffffLL) / 0x40000000LL;  // 32-bit event counters
         li.chunk = (n + epochs - 1) / epochs;
         epochs = (n + li.chunk - 1) / li.chunk;
         if (epochs * (long long)b->R > 0x7fffffffLL) return set_err(KMOS_B200_ERR_ARG, "do_kmc_steps: too many work items");

@@ -481,8 +481,8 @@ def compile_latint_tables(ir):
     nproc = len(ir["procs"])
     n_species = len(ir["species"])
     try:
-        if nproc > 64:
-            raise Unsupported("more than 64 processes")
+        if nproc > 256:
+            raise Unsupported("more than 256 processes")
         offsets = {}
 
         def off_id(o):
@@ -601,8 +601,8 @@ def compile_hbm_tables(ir):
         proc_anchor = proc_anchor_types(ir)
         if any(a == 0 for a in proc_anchor):
             raise Unsupported("a process is registered on several site types")
-        if nproc > 64:
-            raise Unsupported("more than 64 processes")
+        if nproc > 256:
+            raise Unsupported("more than 256 processes")
         if len(ir["species"]) > 16:
             raise Unsupported("more than 16 species")
         offsets = {}

@@ -38,7 +38,9 @@ def rates_for(name, ir, R):
     elif name.startswith("zgb"):
         seeds = max(R // 64, 1)
         r, _g, _d = zgb_grid(ir, seeds=seeds)
-    else:
+    elif ir.get("process_defs"):
         r = np.asarray([rates_mod.model_rates(ir)])
+    else:  # fixtures parsed from committed Fortran carry no rate expressions: unit rate constants
+        r = np.ones((1, len(ir["procs"])))
     reps = -(-R // len(r))
     return np.ascontiguousarray(np.tile(r, (reps, 1))[:R])

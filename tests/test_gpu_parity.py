@@ -49,13 +49,14 @@ def test_local_smart_parity(name, size, R, chunks, kernel):
 
 
 @pytest.mark.parametrize("kernel", ["generic", "warp_hbm"])
-def test_multilattice_pdopd_local_smart_parity(kernel):
-    """Pd(100)/PdO model of the reference's export tests (two lattices, 25 sites per cell, create_/annihilate_
-    routines, a declared null_species): too many sites per cell for the lane tables, so the shared-memory
-    kernel declines and the two HBM-state kernels must match the oracle."""
+@pytest.mark.parametrize("name,size", [("pdopd_local_smart", [6, 5]), ("pairwise84_local_smart", [9, 8])])
+def test_local_smart_models_beyond_the_lane_tables(name, size, kernel):
+    """Models the shared-memory kernel declines: Pd(100)/PdO of the reference's export tests (two lattices, 25
+    sites per cell, create_/annihilate_ routines, a declared null_species) and an 84-process pairwise model
+    (more than 64 processes: 4 process segments per lane).  The two HBM-state kernels must match the oracle."""
     engine = _engine()
-    ir, blob, info = load_model("pdopd_local_smart")
-    R, size, chunks = 6, [6, 5], [3000, 3000]
+    ir, blob, info = load_model(name)
+    R, chunks = 6, [3000, 3000]
     rates, lut, seeds = make_inputs(ir, info, R, seed=11)
     model = engine.Model(ir=ir, blob=blob, info=info)
     auto = engine.Batch(model, R, size, seeds=seeds, rates=rates)
@@ -73,6 +74,7 @@ def test_multilattice_pdopd_local_smart_parity(kernel):
 
 LATINT_CASES = [
     ("pdopd_lat_int", [6, 5], 5, [3000, 3000]),
+    ("pairwise84_lat_int", [12, 11], 6, [3000, 3000]),
     ("ab_lat_int", [10, 12], 6, [1500, 1500]),
     ("mini_101_lat_int", [7, 5], 5, [700, 700]),
     ("zgb_lat_int", [12, 12], 5, [2000, 2000]),

@@ -52,6 +52,7 @@ CASES = [
     ("pairwise_otf_otf", [12, 10], 3000),
     ("pdopd_local_smart", [6, 5], 4000),  # multi-lattice: create_/annihilate_ routines, null_species = 4
     ("pdopd_lat_int", [6, 5], 4000),
+    ("pairwise84_lat_int", [9, 8], 3000),
 ]
 
 

@@ -110,8 +110,16 @@ def project_from_ini(path_or_text):
     return pt
 
 
-def project_from_render_script(path):
-    """Run an examples/render_*.py script, capturing the Project instead of saving XML."""
+def project_from_render_script(path, substitute=None):
+    """Run an examples/render_*.py script, capturing the Project instead of saving XML.
+    substitute: (old, new) text replacement applied to a temporary copy of the script (documented variants)."""
+    if substitute:
+        src = open(path).read()
+        assert substitute[0] in src
+        tmp_script = os.path.join(tempfile.mkdtemp(prefix="render_src_"), os.path.basename(path))
+        with open(tmp_script, "w") as f:
+            f.write(src.replace(substitute[0], substitute[1]))
+        path = tmp_script
     captured = []
     orig_save = kmos.types.Project.save
     orig_action = kmos.types.ConditionAction.__init__
@@ -163,6 +171,13 @@ MODELS = [
     ("ruo2", lambda: project_from_render_script(os.path.join(REF, "examples/render_co_oxidation_ruo2.py")),
      ["local_smart", "lat_int"]),
     ("pairwise", lambda: project_from_render_script(os.path.join(REF, "examples/render_pairwise_interaction.py")),
+     ["lat_int", "local_smart"]),
+    # the same example with three instead of two neighbour states (empty / CO / O): 3 + 3^4 = 84 processes,
+    # a lat_int model beyond 64 processes (4 process segments per lane in the warp kernel)
+    ("pairwise84", lambda: project_from_render_script(
+        os.path.join(REF, "examples/render_pairwise_interaction.py"),
+        substitute=("product(['empty', 'CO'], repeat=len(nn_coords))",
+                    "product(['empty', 'CO', 'O'], repeat=len(nn_coords))")),
      ["lat_int", "local_smart"]),
     ("pairwise_otf",
      lambda: project_from_render_script(os.path.join(REF, "examples/render_pairwise_interaction_otf.py")),

@@ -38,6 +38,11 @@ if __name__ == "__main__":
     cases = {
         "ruo2": [("ruo2_local_smart", [20, 20], 16384, 2000, capi.KERNEL_SMEM),
                  ("ruo2_local_smart", [20, 20], 16384, 200, capi.KERNEL_GENERIC)],
+        "many": [("pairwise84_lat_int", [128, 128], 2048, 2000, capi.KERNEL_WARP_HBM),
+                 ("pairwise84_lat_int", [128, 128], 2048, 200, capi.KERNEL_GENERIC),
+                 ("pairwise84_local_smart", [64, 64], 4096, 2000, capi.KERNEL_WARP_HBM),
+                 ("pdopd_local_smart", [20, 20], 4096, 2000, capi.KERNEL_WARP_HBM),
+                 ("pdopd_local_smart", [20, 20], 4096, 200, capi.KERNEL_GENERIC)],
         "all": [("mini_101_local_smart", [20, 20], 16384, 5000, capi.KERNEL_SMEM),
                 ("zgb_local_smart", [64, 64], 4096, 1000, capi.KERNEL_SMEM),
                 ("ruo2_local_smart", [20, 20], 16384, 2000, capi.KERNEL_SMEM),
