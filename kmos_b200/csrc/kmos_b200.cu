@@ -337,7 +337,7 @@ static void plan_latint(kmos_b200_batch* b) {
     if (m->h.backend == KB_BACKEND_OTF) {
         const int nchunk = (b->g.ncells + KB_OTF_CHUNK - 1) / KB_OTF_CHUNK;
         cudaDeviceProp prop;
-        if (m->h.n_proc <= 32 && (long long)m->h.n_proc * nchunk <= b->g.ncells &&
+        if (m->h.n_proc <= 64 && (long long)m->h.n_proc * nchunk <= b->g.ncells &&
             cudaGetDeviceProperties(&prop, b->device) == cudaSuccess) {
             b->sm_count = prop.multiProcessorCount;
             b->otf_ok = true;

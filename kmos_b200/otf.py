@@ -75,7 +75,10 @@ def user_parameters(ir, overrides=None):
     params = {k: dict(v) for k, v in ir["parameters"].items()}
     for k, v in (overrides or {}).items():
         params.setdefault(k, {})["value"] = v
-    userpar = [evaluate_rate_expression(str(params[name]["value"]), params) for name in ir.get("userpar", [])]
+    # first item of space-separated values: the reference does the same for its deprecated 'lattice_size'
+    # parameter (kmos/run/__init__.py:2417-2428)
+    userpar = [evaluate_rate_expression(str(params[name]["value"]).split(" ")[0], params)
+               for name in ir.get("userpar", [])]
     chempots = []
     for name in ir.get("chempots", []):
         species = name[len("mu_"):]

@@ -106,6 +106,8 @@ OTF_CASES = [
     ("ab_otf", [10, 12], 6, [1500, 1500]),
     ("pairwise_otf_otf", [16, 16], 8, [2000, 2000]),
     ("mini_101_otf", [6, 6], 4, [500, 500]),
+    ("ruo2default_otf", [8, 7], 5, [1500, 1500]),   # the reference's committed otf export: 36 processes, 2 sites/cell
+    ("intzgb_otf", [10, 9], 6, [2000, 2000]),        # interacting ZGB: bystander-dependent rates (1150 LUT entries)
 ]
 
 

@@ -53,6 +53,8 @@ CASES = [
     ("pdopd_local_smart", [6, 5], 4000),  # multi-lattice: create_/annihilate_ routines, null_species = 4
     ("pdopd_lat_int", [6, 5], 4000),
     ("pairwise84_lat_int", [9, 8], 3000),
+    ("ruo2default_otf", [8, 7], 3000),
+    ("intzgb_otf", [10, 9], 3000),
 ]
 
 

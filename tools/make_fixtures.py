@@ -233,17 +233,33 @@ def copy_reference_goldens():
 
 # Fortran the reference itself keeps under version control (byte-golden exports of its own tests): parsed as is.
 GOLDEN_EXPORTS = [
-    ("pdopd", "local_smart", "tests/export_test/reference_pdopd_local_smart"),
-    ("pdopd", "lat_int", "tests/export_test/reference_pdopd_lat_int"),
+    ("pdopd", "local_smart", "tests/export_test/reference_pdopd_local_smart", "tests/export_test/pdopd.xml"),
+    ("pdopd", "lat_int", "tests/export_test/reference_pdopd_lat_int", "tests/export_test/pdopd.xml"),
+    # otf with 36 processes (the RuO2 test model) and with real bystanders (interacting ZGB)
+    ("ruo2default", "otf", "tests/export_test/reference_export_otf", "tests/export_test/default.xml"),
+    ("intzgb", "otf", "tests/export_test/reference_export_intZGB_otf", "tests/export_test/intZGB_otf.xml"),
 ]
 
 
+def xml_parameters(path):
+    """<parameter name= value= adjustable= min= max= scale=/> entries of a kmos project XML (plain ElementTree:
+    the otf rate tables need the user parameters, which the exported Fortran receives only at run time)."""
+    import xml.etree.ElementTree as ET
+    out = {}
+    for p in ET.parse(path).getroot().iter("parameter"):
+        a = p.attrib
+        out[a["name"]] = {"value": a["value"], "adjustable": a.get("adjustable") == "True",
+                          "min": float(a.get("min", 0.0)), "max": float(a.get("max", 0.0)),
+                          "scale": a.get("scale", "linear")}
+    return out
+
+
 def golden_export_fixtures(outdir):
-    for name, backend, rel in GOLDEN_EXPORTS:
+    for name, backend, rel, xml in GOLDEN_EXPORTS:
         ir = fortran_ir.parse_export_dir(os.path.join(REF, rel), backend)
         ir["fixture"] = {"model": name, "backend": backend, "settings_written": False,
                          "generator": "%s (reference, committed Fortran) -> kmos_b200.fortran_ir" % rel}
-        ir.update({"parameters": {}, "process_defs": []})
+        ir.update({"parameters": xml_parameters(os.path.join(REF, xml)), "process_defs": []})
         out = os.path.join(outdir, "%s_%s.json" % (name, backend))
         with open(out, "w") as f:
             json.dump(ir, f, separators=(",", ":"), sort_keys=True)
