@@ -314,3 +314,50 @@ def test_reference_golden_trajectory_replayed_on_the_gpu():
     assert np.array_equal(batch.lattice[0], o.lattice)
     assert np.array_equal(batch.avail_sites(0), o.avail_sites)
     np.testing.assert_allclose(batch.kmc_time[0], o.kmc_time, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name,size,kernel", [
+    ("ruo2_local_smart", [5, 7], "smem"), ("ruo2_local_smart", [5, 7], "warp_hbm"), ("ruo2_local_smart", [5, 7], "generic"),
+    ("zgb_lat_int", [9, 7], "warp_hbm"), ("pairwise_otf_otf", [9, 8], "warp_hbm"), ("ab_local_smart", [4, 3], "smem"),
+])
+def test_many_small_launches_match_one_trajectory(name, size, kernel):
+    """do_kmc_steps(1), (1), (2), ... must walk the same trajectory as the oracle: the persistent schedulers cut
+    a launch into epochs and stage state in and out, so tiny and odd launch sizes are their edge cases (1 step,
+    fewer steps than an epoch, fewer replicas than a CTA holds)."""
+    engine = _engine()
+    ir, blob, info = load_model(name)
+    R = 3
+    rates, lut, seeds = make_inputs(ir, info, R, seed=5)
+    kind = {"smem": capi.KERNEL_SMEM, "generic": capi.KERNEL_GENERIC, "warp_hbm": capi.KERNEL_WARP_HBM}[kernel]
+    batch = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=rates, lut=lut, kernel=kind)
+    assert batch.kernel_info()["kernel_name"] == kernel
+    chunks = [1, 1, 2, 3, 5, 17, 300, 1, 255, 256, 257]
+    gen = run_oracles(blob, size, rates, lut, seeds, chunks)
+    next(gen)
+    for n, oracles in zip(chunks, gen):
+        batch.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(R - 1,))
+    batch.close()
+
+
+@pytest.mark.parametrize("kernel", ["smem", "warp_hbm"])
+def test_epochs_with_replicas_that_stop_midway(kernel, monkeypatch):
+    """A launch cut into several epochs (forced here) while some replicas dead-lock after 36 events: their
+    remaining work items must pass through without touching the state, the others keep stepping."""
+    engine = _engine()
+    monkeypatch.setenv("KMOS_B200_EPOCHS", "5")
+    ir, blob, info = load_model("mini_101_local_smart")
+    R, size = 40, [6, 6]
+    rates = np.tile(np.array([3.0, 2.0]), (R, 1))
+    rates[::3, 1] = 0.0  # adsorption only: the 36 sites fill up, then nothing is available
+    seeds = np.arange(R, dtype=np.uint64) + np.uint64(900)
+    kind = capi.KERNEL_SMEM if kernel == "smem" else capi.KERNEL_WARP_HBM
+    batch = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=rates, kernel=kind)
+    gen = run_oracles(blob, size, rates, None, seeds, [500, 123])
+    next(gen)
+    for n, oracles in zip([500, 123], gen):
+        batch.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(0, 1))
+    assert np.all(batch.status[::3] == capi.REPLICA_DEADLOCK) and np.all(batch.kmc_step[::3] == 36)
+    assert np.all(batch.status[1::3] == 0) and np.all(batch.kmc_step[1::3] == 623)
+    batch.close()
