@@ -27,6 +27,9 @@ SMEM_CASES = [
     ("ruo2_local_smart", [20, 20], 32, [2000, 4000, 6000]),
     ("ruo2_local_smart", [5, 7], 7, [3000, 3000]),
     ("pairwise_local_smart", [10, 9], 9, [2000, 2000]),
+    ("hop3d_local_smart", [5, 6, 5], 7, [2000, 2000]),   # 3-d and 1-d lattices (no reference example has them)
+    ("hop3d_local_smart", [9, 8, 7], 4, [3000]),
+    ("hop1d_local_smart", [17], 6, [2000, 2000]),
 ]
 
 
@@ -73,6 +76,8 @@ def test_local_smart_models_beyond_the_lane_tables(name, size, kernel):
 
 
 LATINT_CASES = [
+    ("hop3d_lat_int", [5, 7, 6], 5, [2000, 2000]),
+    ("hop1d_lat_int", [23], 5, [2000, 2000]),
     ("pdopd_lat_int", [6, 5], 5, [3000, 3000]),
     ("pairwise84_lat_int", [12, 11], 6, [3000, 3000]),
     ("ab_lat_int", [10, 12], 6, [1500, 1500]),
@@ -106,6 +111,7 @@ OTF_CASES = [
     ("ab_otf", [10, 12], 6, [1500, 1500]),
     ("pairwise_otf_otf", [16, 16], 8, [2000, 2000]),
     ("mini_101_otf", [6, 6], 4, [500, 500]),
+    ("hop3d_otf", [5, 6, 5], 5, [1500, 1500]),
     ("ruo2default_otf", [8, 7], 5, [1500, 1500]),   # the reference's committed otf export: 36 processes, 2 sites/cell
     ("intzgb_otf", [10, 9], 6, [2000, 2000]),        # interacting ZGB: bystander-dependent rates (1150 LUT entries)
 ]

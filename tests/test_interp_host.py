@@ -55,6 +55,11 @@ CASES = [
     ("pairwise84_lat_int", [9, 8], 3000),
     ("ruo2default_otf", [8, 7], 3000),
     ("intzgb_otf", [10, 9], 3000),
+    ("hop3d_local_smart", [5, 4, 3], 3000),  # our own 3-d / 1-d hop models: z and 1-d index arithmetic
+    ("hop3d_lat_int", [4, 3, 5], 3000),
+    ("hop3d_otf", [3, 5, 4], 3000),
+    ("hop1d_local_smart", [17], 2000),
+    ("hop1d_lat_int", [23], 2000),
 ]
 
 

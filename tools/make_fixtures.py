@@ -110,6 +110,40 @@ def project_from_ini(path_or_text):
     return pt
 
 
+def project_dim(dim):
+    """A small model of our own for the dimensions the reference's examples do not cover (they are all 2-d):
+    one site per cell, species A / empty, adsorption, desorption and hops to every nearest neighbour along the
+    `dim` axes (so the z and the 1-d index arithmetic of the kernels is exercised)."""
+    from kmos.types import Project, Condition, Action
+    import numpy as np
+    pt = Project()
+    pt.set_meta(author="kmos-b200 tests", email="none@example.org", model_name="hop%dd" % dim, model_dimension=dim)
+    layer = pt.add_layer(name="sc")
+    layer.add_site(name="a")
+    pt.add_species(name="empty", color="#ffffff")
+    pt.add_species(name="A", color="#ff0000", representation="Atoms('O')")
+    pt.species_list.default_species = "empty"
+    pt.add_parameter(name="k_ads", value=1.0, adjustable=True, min=0.1, max=10.0)
+    pt.add_parameter(name="k_des", value=0.7, adjustable=True, min=0.1, max=10.0)
+    pt.add_parameter(name="k_hop", value=2.0, adjustable=True, min=0.1, max=10.0)
+    pt.lattice.cell = np.diag([1.0, 1.0, 1.0])
+    center = pt.lattice.generate_coord("a.(0,0,0).sc")
+    pt.add_process(name="ads", conditions=[Condition(species="empty", coord=center)],
+                   actions=[Action(species="A", coord=center)], rate_constant="k_ads")
+    pt.add_process(name="des", conditions=[Condition(species="A", coord=center)],
+                   actions=[Action(species="empty", coord=center)], rate_constant="k_des")
+    for axis in range(dim):
+        for sign, tag in ((1, "p"), (-1, "m")):
+            off = [0, 0, 0]
+            off[axis] = sign
+            nb = pt.lattice.generate_coord("a.(%d,%d,%d).sc" % tuple(off))
+            pt.add_process(name="hop_%s%s" % ("xyz"[axis], tag),
+                           conditions=[Condition(species="A", coord=center), Condition(species="empty", coord=nb)],
+                           actions=[Action(species="empty", coord=center), Action(species="A", coord=nb)],
+                           rate_constant="k_hop")
+    return pt
+
+
 def project_from_render_script(path, substitute=None):
     """Run an examples/render_*.py script, capturing the Project instead of saving XML.
     substitute: (old, new) text replacement applied to a temporary copy of the script (documented variants)."""
@@ -179,6 +213,8 @@ MODELS = [
         substitute=("product(['empty', 'CO'], repeat=len(nn_coords))",
                     "product(['empty', 'CO', 'O'], repeat=len(nn_coords))")),
      ["lat_int", "local_smart"]),
+    ("hop3d", lambda: project_dim(3), ["local_smart", "lat_int", "otf"]),
+    ("hop1d", lambda: project_dim(1), ["local_smart", "lat_int"]),
     ("pairwise_otf",
      lambda: project_from_render_script(os.path.join(REF, "examples/render_pairwise_interaction_otf.py")),
      ["otf"]),
