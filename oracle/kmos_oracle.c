@@ -604,6 +604,8 @@ int kmos_oracle_run_proc_nr(oracle_t *o, int32_t proc, int32_t site) {
     return o->status;
 }
 void kmos_oracle_update_accum_rate(oracle_t *o) { update_accum_rate(o); }
+/* base.interval_search_real on a caller-supplied array (unit tests): 1-based index, 0 = the reference's `stop` */
+int kmos_oracle_interval_search_real(const double *arr, int32_t size, double value) { return interval_search_real(arr, size, value); }
 
 /* getters */
 int kmos_oracle_volume(const oracle_t *o) { return o->volume; }

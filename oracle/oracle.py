@@ -44,6 +44,8 @@ def lib():
         L.kmos_oracle_get_next_kmc_step.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.kmos_oracle_run_proc_nr.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.kmos_oracle_update_accum_rate.argtypes = [C.c_void_p]
+        L.kmos_oracle_interval_search_real.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_int32, C.c_double]
+        L.kmos_oracle_interval_search_real.restype = C.c_int
         L.kmos_oracle_volume.argtypes = [C.c_void_p]
         L.kmos_oracle_nproc.argtypes = [C.c_void_p]
         L.kmos_oracle_status.argtypes = [C.c_void_p, i32p]
@@ -66,6 +68,12 @@ def lib():
         L.kmos_oracle_philox_step.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, f64p]
         _lib = L
     return _lib
+
+
+def interval_search_real(arr, value):
+    """base.interval_search_real (base.mpy:1234-1338) on a float64 array: 1-based index, 0 where the reference stops."""
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    return int(lib().kmos_oracle_interval_search_real(a, a.size, float(value)))
 
 
 def philox_step(seed, replica, step):

@@ -22,6 +22,11 @@ struct Harness {
 
 extern "C" {
 
+// KbInterp::interval_search_real, the routine the CUDA kernels compile (unit tests)
+int kbh_interval_search_real(const double* arr, int size, double value) {
+    return KbInterp<uint16_t>::interval_search_real(arr, size, value);
+}
+
 Harness* kbh_create(const int32_t* blob, int64_t n, const int32_t size[3], uint64_t seed, uint32_t replica) {
     Harness* h = new Harness;
     h->blob.assign(blob, blob + n);

@@ -105,3 +105,58 @@ def test_host_build_of_cuda_interpreter_matches_oracle(harness, name, size, step
     assert L.kbh_set_configuration(h, spec, int(blob[9])) == 0
     compare()
     L.kbh_destroy(h)
+
+
+def _interval_search_by_the_book(arr, value):
+    """base.interval_search_real transliterated statement by statement (kmos/fortran_src/base.mpy:1234-1338),
+    1-based; returns 0 where the Fortran prints its dead-lock message and stops (or walks off the array)."""
+    n = len(arr)
+    left, right = 1, n
+    while True:
+        mid = (right + left) >> 1          # ISHFT(right+left, -1), computed before the exit test
+        if left >= right:
+            break
+        if value < arr[mid - 1]:
+            right = mid
+        else:
+            left = mid + 1
+    if arr[mid - 1] == 0.0:                # nonzerosearch
+        while True:
+            if mid > n:
+                return 0
+            if arr[mid - 1] > 0.0:
+                if mid >= n:
+                    return 0
+                break
+            mid += 1
+    while mid != 1 and arr[mid - 2] >= arr[mid - 1]:   # leftmostsearch
+        mid -= 1
+    return mid
+
+
+def test_interval_search_real_edge_cases(harness):
+    """The reference has no unit test for this routine although its docstring asks for one (base.mpy:1253-1255).
+    Three implementations must agree: the transliteration above, the oracle's C, and the routine the CUDA kernels
+    compile (KbInterp::interval_search_real, built for the host) -- on plateaus (zero-rate processes), leading
+    and trailing zeros, values exactly on an entry, value == last entry (ran = 1 cannot occur, but 0 can)."""
+    harness.kbh_interval_search_real.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_int, C.c_double]
+    harness.kbh_interval_search_real.restype = C.c_int
+    rng = np.random.RandomState(12)
+    cases = [([1.0], [0.0, 0.5, 1.0]), ([0.0, 0.0, 2.0, 2.0, 5.0], [0.0, 1.9, 2.0, 4.999, 5.0]),
+             ([3.0, 3.0, 3.0], [0.0, 2.9, 3.0]), ([0.0, 0.0, 0.0], [0.0]), ([0.0, 0.0, 7.0], [0.0, 6.0]),
+             ([1.0, 1.0, 4.0, 4.0, 4.0, 9.0, 9.0], [0.0, 0.999, 1.0, 3.9, 4.0, 8.9, 9.0])]
+    for _ in range(300):
+        n = rng.randint(1, 40)
+        inc = rng.choice([0.0, 0.0, 1.0, 0.25, 3.0], size=n) * rng.uniform(0.5, 2.0, size=n)
+        arr = np.cumsum(inc)
+        vals = list(rng.uniform(0, 1, 6) * arr[-1]) + list(arr[rng.randint(0, n, 3)]) + [0.0]
+        cases.append((list(arr), vals))
+    checked = 0
+    for arr, vals in cases:
+        a = np.asarray(arr, dtype=np.float64)
+        for v in vals:
+            want = _interval_search_by_the_book(arr, v)
+            assert oracle.interval_search_real(a, v) == want, (arr, v)
+            assert harness.kbh_interval_search_real(a, a.size, float(v)) == want, (arr, v)
+            checked += 1
+    assert checked > 2500

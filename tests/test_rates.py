@@ -1,0 +1,56 @@
+"""Host-side rate preparation: kmos_b200.rates.evaluate_rate_expression mirrors kmos.evaluate_rate_expression
+(kmos/__init__.py:67-189).  The vectors of the reference's own tests/test_evaluate_rate_expression.py are restated
+here; where the reference checkout is importable (this container, not the GPU box) the two implementations are
+also run side by side on every rate expression of the RuO2 / ZGB / pairwise fixtures that needs no JANAF data."""
+import math
+import os
+import sys
+
+import pytest
+
+from conftest import REPO, load_model
+from kmos_b200 import rates
+
+REF = "/root/reference"
+
+
+def test_reference_unit_vectors():
+    ev = rates.evaluate_rate_expression
+    assert ev("1.5e-3") == pytest.approx(1.5e-3)
+    assert ev("2 * 3 + 4") == pytest.approx(10.0)
+    assert ev("exp(1)") == pytest.approx(math.e, rel=1e-12)
+    assert ev("T * 2", {"T": {"value": 600}, "p_CO": {"value": 1.0}}) == pytest.approx(1200.0)
+    assert ev("kboltzmann * 600") == pytest.approx(1.3806488e-23 * 600, rel=1e-6)
+    r = ev("1/(beta*h)*exp(-beta*0.9*eV)", {"T": {"value": 600}})
+    assert 0 < r < 1e20
+    assert ev("") == 0.0
+
+
+def test_model_rates_are_finite_and_positive():
+    for name in ("ruo2_local_smart", "zgb_local_smart", "pairwise_lat_int", "ab_local_smart"):
+        ir, _blob, _info = load_model(name)
+        r = rates.model_rates(ir)
+        assert len(r) == len(ir["procs"]) and all(math.isfinite(x) and x >= 0 for x in r)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "kmos")), reason="reference checkout absent")
+def test_side_by_side_with_the_reference_implementation():
+    sys.path.insert(0, os.path.join(REPO, "tools", "ase_shim"))
+    sys.path.insert(0, REF)
+    try:
+        import kmos
+    finally:
+        sys.path.remove(REF)
+    checked = 0
+    for name in ("ruo2_local_smart", "zgb_local_smart", "pairwise_lat_int", "ab_local_smart"):
+        ir, _blob, _info = load_model(name)
+        params = {k: {"value": v["value"]} for k, v in ir["parameters"].items()}
+        for p in ir["process_defs"]:
+            expr = p["rate_constant"]
+            if not expr or "mu_" in expr:  # mu_* needs the JANAF tables, which are not vendored
+                continue
+            ours = rates.evaluate_rate_expression(expr, params)
+            ref = kmos.evaluate_rate_expression(rate_expr=expr, parameters=params)
+            assert ours == pytest.approx(ref, rel=1e-13), (name, p["name"], expr)
+            checked += 1
+    assert checked >= 40
