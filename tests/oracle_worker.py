@@ -13,8 +13,9 @@ def main(fin, fout):
     d = np.load(fin)
     blob, size, chunks = d["blob"], [int(x) for x in d["size"]], [int(x) for x in d["chunks"]]
     lat, ps, tm, st, ok = [], [], [], [], []
-    for seed, rid, rt in zip(d["seeds"], d["ids"], d["rates"]):
-        o = oracle.Oracle(blob, size, seed=int(seed), replica=int(rid), rates=rt)
+    luts = d["lut"] if "lut" in d.files else [None] * len(d["ids"])
+    for seed, rid, rt, lt in zip(d["seeds"], d["ids"], d["rates"], luts):
+        o = oracle.Oracle(blob, size, seed=int(seed), replica=int(rid), rates=rt, lut=lt)
         rows = ([], [], [], [], [])
         for n in chunks:
             o.do_steps(n)

@@ -47,7 +47,7 @@ def compare_batch(batch, oracles, avail_replicas=(0,), time_rtol=1e-12, integ_rt
             assert np.array_equal(batch.avail_sites(r), oracles[r].avail_sites), "avail_sites differ (replica %d)" % r
 
 
-def oracle_checkpoints(blob, size, seeds, rates, chunks, workers, timeout=600):
+def oracle_checkpoints(blob, size, seeds, rates, chunks, workers, timeout=600, lut=None):
     """Oracle trajectories of len(seeds) replicas on `workers` host processes (tests/oracle_worker.py started
     with subprocess: independent of this process' CUDA context, bounded by `timeout` seconds).
     -> (lattice[R][C][V] int8, procstat[R][C][P], kmc_time[R][C], kmc_step[R][C], status[R][C])."""
@@ -63,8 +63,9 @@ def oracle_checkpoints(blob, size, seeds, rates, chunks, workers, timeout=600):
         for w in range(workers):
             ids = np.arange(w, R, workers)
             fin, fout = os.path.join(tmp, "in%d.npz" % w), os.path.join(tmp, "out%d.npz" % w)
+            extra = {} if lut is None else {"lut": np.asarray(lut)[ids]}
             np.savez(fin, blob=blob, size=np.asarray(size), seeds=np.asarray(seeds)[ids], ids=ids,
-                     rates=np.asarray(rates)[ids], chunks=np.asarray(chunks))
+                     rates=np.asarray(rates)[ids], chunks=np.asarray(chunks), **extra)
             procs.append((ids, fout, subprocess.Popen([sys.executable, os.path.join(here, "oracle_worker.py"), fin, fout])))
         out = None
         for ids, fout, p in procs:
