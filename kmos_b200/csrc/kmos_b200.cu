@@ -85,6 +85,7 @@ struct kmos_b200_batch {
     bool li_ok;  // warp-per-replica lat_int kernel available
     KbLatintParams li;
     int li_wpc, li_smem_bytes, li_mode;  // li_mode 0: lat_int decision trees, 1: local_smart flattened ops
+    int li_lat_bytes;                    // > 0: bytes per warp of the 4-bit lattice copy in shared memory (else 0)
 };
 
 extern "C" const char* kmos_b200_last_error(void) { return g_err.c_str(); }
@@ -379,6 +380,21 @@ static void plan_latint(kmos_b200_batch* b) {
     if (li_ppl >= 4) {  // the kernels for more than 64 processes read their tables in place (kb_latint.cuh)
         li.tab_bytes = 0;
         b->li_smem_bytes = b->li_wpc * li.rep_bytes;
+    }
+    // lattice copy in shared memory (4 bits per site): the probes of an event are chains of dependent lattice
+    // reads.  Taken when as many CTAs stay resident as the batch can use (at most 3, what the registers allow).
+    b->li_lat_bytes = 0;
+    if (li_ppl <= 2 && m->h.n_species <= 15 && !getenv("KMOS_B200_NO_LATS")) {
+        const int lat_bytes = (int)align_up((size_t)((b->g.volume + 7) / 8) * 4, 16);
+        const int with_lat = li.tab_bytes + b->li_wpc * (li.rep_bytes + lat_bytes);
+        int needed = (b->R + b->li_wpc * prop.multiProcessorCount - 1) / (b->li_wpc * prop.multiProcessorCount);
+        if (needed > 3) needed = 3;
+        if (with_lat <= (int)prop.sharedMemPerBlockOptin &&
+            (int)(prop.sharedMemPerMultiprocessor / (size_t)(with_lat + 1024)) >= needed) {
+            b->li_lat_bytes = lat_bytes;
+            li.rep_bytes += lat_bytes;
+            b->li_smem_bytes = with_lat;
+        }
     }
     if (b->li_smem_bytes > (int)prop.sharedMemPerBlockOptin) return;
     li.n_proc = m->h.n_proc; li.n_species = m->h.n_species; li.spuck = m->h.spuck; li.dim = m->h.dim;
@@ -868,10 +884,13 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         const bool dense = (long long)b->R > 24LL * b->sm_count;  // more replicas than 3 CTAs/SM can hold
         // PPL: processes per lane.  Up to 64 processes the register budget is tuned per occupancy (MINB 3/4);
         // 65..256 processes carry 4 or 8 rate/integral/prefix registers per lane and run 2 CTAs per SM.
-#define KB_LI(PPLV, IDX, MODEV) (dense ? kb_latint_kernel<PPLV, IDX, MODEV, 4> : kb_latint_kernel<PPLV, IDX, MODEV, 3>)
+#define KB_LI(PPLV, IDX, MODEV)                                                                                 \
+        (lats ? (dense ? kb_latint_kernel<PPLV, IDX, MODEV, 4, true> : kb_latint_kernel<PPLV, IDX, MODEV, 3, true>) \
+              : (dense ? kb_latint_kernel<PPLV, IDX, MODEV, 4, false> : kb_latint_kernel<PPLV, IDX, MODEV, 3, false>))
 #define KB_LI_MODE(IDX, MODEV)                                               \
         (np <= 32 ? KB_LI(1, IDX, MODEV) : np <= 64 ? KB_LI(2, IDX, MODEV)   \
-                  : np <= 128 ? kb_latint_kernel<4, IDX, MODEV, 2> : kb_latint_kernel<8, IDX, MODEV, 2>)
+                  : np <= 128 ? kb_latint_kernel<4, IDX, MODEV, 2, false> : kb_latint_kernel<8, IDX, MODEV, 2, false>)
+        const bool lats = b->li_lat_bytes > 0;
         if (b->li_mode == 0) fn = b->idx32 ? KB_LI_MODE(uint32_t, 0) : KB_LI_MODE(uint16_t, 0);
         else fn = b->idx32 ? KB_LI_MODE(uint32_t, 1) : KB_LI_MODE(uint16_t, 1);
 #undef KB_LI_MODE
