@@ -282,7 +282,7 @@ struct KbCellCtx {
 //   w1 = class base (cls * ncells) | first slot of the list (arena*cap, or arena*cap + cap-1 if it grows down) << 16
 //   then ncond probe words off_id | n<<5 | mask<<8
 template <int PPL, int NCOND, bool SPLIT, bool P1G, bool NBT>
-__global__ void __launch_bounds__(P1G ? 768 : 640) kb_smem_kernel(const KbSmemParams prm) {
+__global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
     extern __shared__ __align__(128) unsigned char kb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
