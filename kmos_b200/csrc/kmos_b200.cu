@@ -515,14 +515,15 @@ static void plan_smem(kmos_b200_batch* b) {
     b->smem_ok = true;
 }
 
-// Shared-memory kernel vs HBM-resident warp kernel: measured per-warp speeds are about 1 : 0.65 : 0.26
-// (all-shared : lists in L2 : everything in HBM), so the HBM kernel wins when shared memory can host only a
-// few replicas per SM (ZGB 64x64: 7 vs 24 warps per SM).
+// Shared-memory kernel vs HBM-resident warp kernel: measured per-warp speeds are about 1 : 0.67 : 0.5
+// (all-shared : lists in L2 : everything in HBM with the lattice copy in shared memory; RuO2 20x20 1.21e9 vs
+// 9.4e8 at 24 warps per SM each), so the HBM kernel wins when shared memory can host fewer than about half of
+// the 24 warps it keeps resident itself (ZGB 64x64: 7 warps per SM, 4.7e8 vs 1.06e9).
 static int auto_kernel(const kmos_b200_batch* b) {
     if (b->smem_ok && b->li_ok) {
         double hbm_warps = (double)b->R / (double)(b->sm_count > 0 ? b->sm_count : 1);
-        if (hbm_warps > 32.0) hbm_warps = 32.0;
-        return (0.26 * hbm_warps > b->smem_score) ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_SMEM;
+        if (hbm_warps > 24.0) hbm_warps = 24.0;
+        return (0.5 * hbm_warps > b->smem_score) ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_SMEM;
     }
     if (b->smem_ok) return KMOS_B200_KERNEL_SMEM;
     return (b->li_ok || b->otf_ok) ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC;
@@ -881,12 +882,11 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         const int threads = b->li_wpc * 32;
         void (*fn)(const KbLatintParams);
         const int np = b->model->h.n_proc;
-        const bool dense = (long long)b->R > 24LL * b->sm_count;  // more replicas than 3 CTAs/SM can hold
-        // PPL: processes per lane.  Up to 64 processes the register budget is tuned per occupancy (MINB 3/4);
+        // PPL: processes per lane.  Up to 64 processes: 80 registers, 3 CTAs per SM (the 64-register variant for
+        // 4 CTAs spills and measured 2-14 % slower even with more replicas than 24 per SM waiting);
         // 65..256 processes carry 4 or 8 rate/integral/prefix registers per lane and run 2 CTAs per SM.
-#define KB_LI(PPLV, IDX, MODEV)                                                                                 \
-        (lats ? (dense ? kb_latint_kernel<PPLV, IDX, MODEV, 4, true> : kb_latint_kernel<PPLV, IDX, MODEV, 3, true>) \
-              : (dense ? kb_latint_kernel<PPLV, IDX, MODEV, 4, false> : kb_latint_kernel<PPLV, IDX, MODEV, 3, false>))
+#define KB_LI(PPLV, IDX, MODEV) \
+        (lats ? kb_latint_kernel<PPLV, IDX, MODEV, 3, true> : kb_latint_kernel<PPLV, IDX, MODEV, 3, false>)
 #define KB_LI_MODE(IDX, MODEV)                                               \
         (np <= 32 ? KB_LI(1, IDX, MODEV) : np <= 64 ? KB_LI(2, IDX, MODEV)   \
                   : np <= 128 ? kb_latint_kernel<4, IDX, MODEV, 2, false> : kb_latint_kernel<8, IDX, MODEV, 2, false>)

@@ -38,6 +38,16 @@ if __name__ == "__main__":
     cases = {
         "ruo2": [("ruo2_local_smart", [20, 20], 16384, 2000, capi.KERNEL_SMEM),
                  ("ruo2_local_smart", [20, 20], 16384, 200, capi.KERNEL_GENERIC)],
+        "planner": [("ruo2_local_smart", [20, 20], 16384, 2000, capi.KERNEL_SMEM),
+                    ("ruo2_local_smart", [20, 20], 16384, 2000, capi.KERNEL_WARP_HBM),
+                    ("zgb_local_smart", [64, 64], 4096, 2000, capi.KERNEL_SMEM),
+                    ("zgb_local_smart", [64, 64], 4096, 2000, capi.KERNEL_WARP_HBM),
+                    ("zgb_local_smart", [32, 32], 8192, 2000, capi.KERNEL_SMEM),
+                    ("zgb_local_smart", [32, 32], 8192, 2000, capi.KERNEL_WARP_HBM),
+                    ("ab_local_smart", [20, 20], 16384, 4000, capi.KERNEL_SMEM),
+                    ("ab_local_smart", [20, 20], 16384, 4000, capi.KERNEL_WARP_HBM),
+                    ("pairwise_local_smart", [30, 30], 8192, 2000, capi.KERNEL_SMEM),
+                    ("pairwise_local_smart", [30, 30], 8192, 2000, capi.KERNEL_WARP_HBM)],
         "many": [("pairwise84_lat_int", [128, 128], 2048, 2000, capi.KERNEL_WARP_HBM),
                  ("pairwise84_lat_int", [128, 128], 2048, 200, capi.KERNEL_GENERIC),
                  ("pairwise84_local_smart", [64, 64], 4096, 2000, capi.KERNEL_WARP_HBM),
