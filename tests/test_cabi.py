@@ -69,3 +69,21 @@ def test_philox_hook_matches_oracle_cpu(built):
     for seed, rep, step in [(1, 0, 0), (2**40 + 17, 123, 2**33 + 5)]:
         ref = oracle.philox_step(seed, rep, step)
         assert list(ref) == [L.kmos_b200_philox_next(seed, rep, step, s) for s in range(3)]
+
+
+def test_fortran_interface_block_matches_the_header():
+    """INTEGRATION.md section 3 (ISO_C_BINDING interface for the template-side proclist): every bind(C) name must be
+    an exported symbol and take as many arguments as the C declaration (no Fortran compiler here to check more)."""
+    import re
+    text = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    block = text[text.index("module kmos_b200_c"):text.index("end module")]
+    header = open(os.path.join(REPO, "include", "kmos_b200.h")).read()
+    funcs = re.findall(r"function\s+(\w+)\s*\(([^)]*)\)\s*&?\s*bind\(C,\s*name=\"(\w+)\"\)", block, re.S)
+    assert len(funcs) >= 6
+    for fname, fargs, cname in funcs:
+        assert fname == cname and cname in capi.EXPORTED, cname
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % cname, header, re.S)
+        assert m, "not declared in the header: %s" % cname
+        n_c = 0 if m.group(1).strip() in ("", "void") else m.group(1).count(",") + 1
+        n_f = len([a for a in fargs.replace("&", "").split(",") if a.strip()])
+        assert n_c == n_f, (cname, n_c, n_f)
