@@ -360,10 +360,14 @@ static void plan_latint(kmos_b200_batch* b) {
     if (cudaGetDeviceProperties(&prop, b->device) != cudaSuccess) return;
     // distinct offsets of one event must be distinct cells (the generated code assumes it too: folded probes,
     // one list operation per (process, cell)): no aliasing under periodic wrap
+    int max_off[3] = {0, 0, 0};
     for (int i = 0; i < d[8]; ++i) {
         uint32_t w = (uint32_t)d[d[7] + i];
-        for (int a = 0; a < m->h.dim; ++a)
-            if (2 * abs((int)(int8_t)((w >> (8 * a)) & 255u)) >= b->g.size[a]) return;
+        for (int a = 0; a < m->h.dim; ++a) {
+            const int o = abs((int)(int8_t)((w >> (8 * a)) & 255u));
+            if (2 * o >= b->g.size[a]) return;
+            if (o > max_off[a]) max_off[a] = o;
+        }
     }
     int Lx = b->g.size[0], LxLy = b->g.size[0] * b->g.size[1];
     if (Lx == 1 || LxLy == 1) return;
@@ -398,6 +402,17 @@ static void plan_latint(kmos_b200_batch* b) {
     }
     if (b->li_smem_bytes > (int)prop.sharedMemPerBlockOptin) return;
     li.n_proc = m->h.n_proc; li.n_species = m->h.n_species; li.spuck = m->h.spuck; li.dim = m->h.dim;
+    // an event's probes reach two offsets from its cell (an op's anchor plus that op's own probes)
+    for (int a = 0; a < 3; ++a) li.margin[a] = a < m->h.dim ? 2 * max_off[a] : 0;
+    {   // worth it for the decision-tree walks of lat_int on lattices that are mostly interior (128x128: 94 %);
+        // the local_smart instantiations compile without it (kb_latint.cuh), small lattices switch it off here
+        double frac = 1.0;
+        for (int a = 0; a < m->h.dim; ++a) frac *= (double)std::max(0, b->g.size[a] - 2 * li.margin[a]) / b->g.size[a];
+        const char* ienv = getenv("KMOS_B200_INTERIOR");  // 1: whenever a cell qualifies, 0: never (parity tests)
+        const bool on = ienv ? atoi(ienv) != 0 : frac >= 0.8;
+        if (b->li_mode != 0 || !on)
+            for (int a = 0; a < 3; ++a) li.margin[a] = 1 << 20;  // no cell counts as interior
+    }
     for (int a = 0; a < 3; ++a) li.size[a] = b->g.size[a];
     li.ncells = b->g.ncells;
     b->sm_count = prop.multiProcessorCount;

@@ -107,6 +107,26 @@ def test_lat_int_parity(name, size, R, chunks, kernel):
     batch.close()
 
 
+@pytest.mark.parametrize("name,size,R,chunks", LATINT_CASES + [("pairwise_lat_int", [24, 20], 6, [3000, 3000])])
+def test_lat_int_interior_cells(name, size, R, chunks, monkeypatch):
+    """The warp-HBM kernel addresses the probes of events away from the lattice edges without the periodic
+    arithmetic (cell + linear offset).  The planner enables that for mostly-interior lattices only (128x128);
+    forced on here so that small lattices mix interior and edge events, 1-d to 3-d."""
+    engine = _engine()
+    monkeypatch.setenv("KMOS_B200_INTERIOR", "1")
+    ir, blob, info = load_model(name)
+    rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + 7)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=capi.KERNEL_WARP_HBM)
+    assert batch.kernel_info()["kernel_name"] == "warp_hbm"
+    gen = run_oracles(blob, size, rates, lut, seeds, chunks)
+    next(gen)
+    for n, oracles in zip(chunks, gen):
+        batch.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(0, R - 1))
+    batch.close()
+
+
 OTF_CASES = [
     ("ab_otf", [10, 12], 6, [1500, 1500]),
     ("pairwise_otf_otf", [16, 16], 8, [2000, 2000]),
