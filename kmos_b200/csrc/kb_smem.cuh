@@ -132,6 +132,17 @@ __device__ __forceinline__ void kb_st_release(int* p, int v) {
 
 __device__ __forceinline__ int kb_s8(uint32_t w, int shift) { return (int)(int8_t)((w >> shift) & 255u); }
 
+__device__ __forceinline__ unsigned kb_lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ unsigned kb_lanemask_le() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
 // slot index of position k (0-based) of a list inside its arena
 __device__ __forceinline__ int kb_slot(int arena, int dir, int cap, int k) {
     return arena * cap + (dir ? cap - 1 - k : k);
@@ -439,16 +450,27 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
         // Lane L must end up with accum_rates(L+1) = ((x_0 + x_1) + ...) + x_L.  The products sit behind len1
         // leading zeros; lane L starts L+1 entries in, so after len1 additions it has added zeros (exact)
         // followed by x_0..x_L in order -- no per-lane masking, one LDS + one DADD per process.
-        if (has0) Z1[len1 + q0] = pr0;
+        // Full first segment (len1 == 32, e.g. RuO2's 36 processes): most products are zero at any time (RuO2
+        // sweep: 7 of 36 non-zero on average) and adding 0.0 is exact, so the non-zero products are packed in
+        // process order and lane L adds the first popc(nz & lanes <= L) of them: the chain is as long as the
+        // number of non-zero products, rounded up to 4 with leading zeros, instead of 32.
+        const unsigned nz0 = (len1 == 32) ? __ballot_sync(KB_FULL, pr0 != 0.0) : 0u;
+        if (len1 == 32) {
+            if (pr0 != 0.0) Z1[32 + __popc(nz0 & kb_lanemask_lt())] = pr0;
+        } else if (has0) {
+            Z1[len1 + q0] = pr0;
+        }
         if (has1) Z2[len2 + lane] = pr1;
         __syncwarp();
         double acc0 = 0.0;
         {
-            const double* src = Z1 + lane + 1;
-            if (len1 == 32) {  // the common full-warp case, completely unrolled
-#pragma unroll
-                for (int t = 0; t < 32; ++t) acc0 = __dadd_rn(acc0, src[t]);
+            if (len1 == 32) {
+                const int mm = (__popc(nz0) + 3) & ~3;
+                const double* src = Z1 + 32 + __popc(nz0 & kb_lanemask_le()) - mm;
+                for (int t = 0; t < mm; t += 4)
+                    acc0 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc0, src[t]), src[t + 1]), src[t + 2]), src[t + 3]);
             } else {
+                const double* src = Z1 + lane + 1;
                 for (int t = 0; t < len1; t += 2) acc0 = __dadd_rn(__dadd_rn(acc0, src[t]), src[t + 1]);
             }
         }
