@@ -452,8 +452,8 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
         // followed by x_0..x_L in order -- no per-lane masking, one LDS + one DADD per process.
         // Full first segment (len1 == 32, e.g. RuO2's 36 processes): most products are zero at any time (RuO2
         // sweep: 7 of 36 non-zero on average) and adding 0.0 is exact, so the non-zero products are packed in
-        // process order and lane L adds the first popc(nz & lanes <= L) of them: the chain is as long as the
-        // number of non-zero products, rounded up to 4 with leading zeros, instead of 32.
+        // process order and lane L adds the first popc(nz & lanes <= L) of them: the chain covers the
+        // non-zero products only (8, 16 or 32 additions, leading zeros make up the difference).
         const unsigned nz0 = (len1 == 32) ? __ballot_sync(KB_FULL, pr0 != 0.0) : 0u;
         if (len1 == 32) {
             if (pr0 != 0.0) Z1[32 + __popc(nz0 & kb_lanemask_lt())] = pr0;
@@ -465,10 +465,22 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
         double acc0 = 0.0;
         {
             if (len1 == 32) {
-                const int mm = (__popc(nz0) + 3) & ~3;
-                const double* src = Z1 + 32 + __popc(nz0 & kb_lanemask_le()) - mm;
-                for (int t = 0; t < mm; t += 4)
-                    acc0 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc0, src[t]), src[t + 1]), src[t + 2]), src[t + 3]);
+                // chain length in tiers (8, 16, 32: straight-line code, leading zeros make up the difference)
+                const int c0 = __popc(nz0);
+                const double* top = Z1 + 32 + __popc(nz0 & kb_lanemask_le());
+                if (c0 <= 8) {
+                    const double* src = top - 8;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) acc0 = __dadd_rn(acc0, src[t]);
+                } else if (c0 <= 16) {
+                    const double* src = top - 16;
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) acc0 = __dadd_rn(acc0, src[t]);
+                } else {
+                    const double* src = top - 32;
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) acc0 = __dadd_rn(acc0, src[t]);
+                }
             } else {
                 const double* src = Z1 + lane + 1;
                 for (int t = 0; t < len1; t += 2) acc0 = __dadd_rn(__dadd_rn(acc0, src[t]), src[t + 1]);
@@ -478,7 +490,12 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
         if (PPL == 2) {
             acc1 = __shfl_sync(KB_FULL, acc0, 31);  // accum_rates(32)
             const double* src = Z2 + lane + 1;
-            for (int t = 0; t < len2; t += 2) acc1 = __dadd_rn(__dadd_rn(acc1, src[t]), src[t + 1]);
+            if (len2 == 4) {  // 35 or 36 processes (RuO2): straight-line, no generic unrolled loop with its remainders
+                acc1 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc1, src[0]), src[1]), src[2]), src[3]);
+            } else {
+#pragma unroll 1
+                for (int t = 0; t < len2; t += 2) acc1 = __dadd_rn(__dadd_rn(acc1, src[t]), src[t + 1]);
+            }
         }
         const double total = __shfl_sync(KB_FULL, (PPL == 2 && lastp >= 32) ? acc1 : acc0, lastp & 31);
         if (!(total > 0.0)) { status = KB_DEADLOCK; break; }
@@ -523,6 +540,16 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
         {
             const uint32_t w = reinterpret_cast<const uint32_t*>(events + 2 * pidx + 1)[lane & 3];  // lane < 4: its write
             const int wcell = __shfl_sync(KB_FULL, nb, (int)(w & 31u));
+#ifdef KB_EXP_WR
+            {
+                const bool wr = lane < n_writes;
+                const int idx = wr ? wcell * spuck + (int)((w >> 5) & 7u) - 1 : 0;
+                const int found = lat[idx], oldsp = (int)((w >> 8) & 15u), newsp = (int)((w >> 12) & 15u);
+                const bool bad = wr && found != oldsp;  // replace_species consistency check (base.mpy:1205)
+                if (bad) status = KB_SPECIES_MISMATCH;
+                if (wr && !bad) lat[idx] = (uint8_t)newsp;
+            }
+#else
             if (lane < n_writes) {
                 const int idx = wcell * spuck + (int)((w >> 5) & 7u) - 1;
                 const int found = lat[idx], oldsp = (int)((w >> 8) & 15u), newsp = (int)((w >> 12) & 15u);
@@ -532,6 +559,7 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
                     lat[idx] = (uint8_t)newsp;
                 }
             }
+#endif
         }
         // cumulative op counts of the rounds, one byte each; bytes past the last round repeat the total
         unsigned long long ends = ((unsigned long long)eh.z << 32) | eh.y;
@@ -581,27 +609,28 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
                     ok = ok && (((cw[j] >> 8) >> sp) & 1u);
                 }
             }
-            if (ok) {
-                if (h & 1u) {  // add_proc (base.mpy:268-302)
-                    if (nq >= C || entry[ca] != 0) {
-                        status = KB_CAPACITY;
-                    } else {
-                        kb_p1_set<SPLIT>(p1, p1hi, down ? slot0 - nq : slot0 + nq, ca);
-                        entry[ca] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)(nq + 1));
-                        *nSq = nq + 1;
-                    }
-                } else {  // guarded del_proc (base.mpy:211-265)
-                    const uint32_t e = entry[ca];
-                    if ((e >> KB_POS_BITS) == member) {
-                        const int pos = (int)(e & KB_POS_MASK);
-                        if (!P1G) last = kb_p1_get<SPLIT>(p1, p1hi, down ? slot0 - (nq - 1) : slot0 + (nq - 1));
-                        if (pos < nq) {
-                            kb_p1_set<SPLIT>(p1, p1hi, down ? slot0 - (pos - 1) : slot0 + (pos - 1), last);
-                            entry[last] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)pos);
-                        }
-                        entry[ca] = 0;
-                        *nSq = nq - 1;
-                    }
+            {
+                // add_proc (base.mpy:268-302) and the guarded del_proc (base.mpy:211-265) as one predicated
+                // sequence: a round usually mixes both, and the divergent branches cost more than the stores
+                const uint32_t e = entry[ca];  // idle lanes read a valid entry (class base 0, lane 0's cell)
+                const bool is_add = h & 1u;
+                const bool add_bad = ok && is_add && (nq >= C || e != 0);
+                const bool add_go = ok && is_add && !add_bad;
+                const bool del_go = ok && !is_add && (e >> KB_POS_BITS) == member;
+                const int pos = (int)(e & KB_POS_MASK);
+                if (!P1G) {
+                    if (del_go) last = kb_p1_get<SPLIT>(p1, p1hi, down ? slot0 - (nq - 1) : slot0 + (nq - 1));
+                }
+                const bool move = del_go && pos < nq;  // the last element takes the freed position
+                if (add_bad) status = KB_CAPACITY;
+                if (add_go || move) {
+                    const int kk = add_go ? nq : pos - 1;
+                    kb_p1_set<SPLIT>(p1, p1hi, down ? slot0 - kk : slot0 + kk, add_go ? ca : last);
+                }
+                if (move) entry[last] = (uint16_t)((member << KB_POS_BITS) | (uint32_t)pos);
+                if (add_go || del_go) {
+                    entry[ca] = add_go ? (uint16_t)((member << KB_POS_BITS) | (uint32_t)(nq + 1)) : (uint16_t)0;
+                    *nSq = add_go ? nq + 1 : nq - 1;
                 }
             }
             // -- rotate
