@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
 
     // ---- per-lane process registers -----------------------------------------------------------------
     const int q0 = lane, q1 = lane + 32;
-    const bool has0 = q0 < P, has1 = (PPL == 2) && (q1 < P);
+    const bool has0 = (PPL == 2) || q0 < P, has1 = (PPL == 2) && (q1 < P);  // PPL == 2: more than 32 processes
     const double rate0 = has0 ? prm.rates[(size_t)rep * P + q0] : 0.0;
     const double rate1 = has1 ? prm.rates[(size_t)rep * P + q1] : 0.0;
     double integ0 = has0 ? prm.integ[(size_t)rep * P + q0] : 0.0;
@@ -454,8 +454,9 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
         // sweep: 7 of 36 non-zero on average) and adding 0.0 is exact, so the non-zero products are packed in
         // process order and lane L adds the first popc(nz & lanes <= L) of them: the chain covers the
         // non-zero products only (8, 16 or 32 additions, leading zeros make up the difference).
-        const unsigned nz0 = (len1 == 32) ? __ballot_sync(KB_FULL, pr0 != 0.0) : 0u;
-        if (len1 == 32) {
+        const bool full1 = (PPL == 2) || len1 == 32;  // compile-time for the two-segment instantiations
+        const unsigned nz0 = full1 ? __ballot_sync(KB_FULL, pr0 != 0.0) : 0u;
+        if (full1) {
             if (pr0 != 0.0) Z1[32 + __popc(nz0 & kb_lanemask_lt())] = pr0;
         } else if (has0) {
             Z1[len1 + q0] = pr0;
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
         __syncwarp();
         double acc0 = 0.0;
         {
-            if (len1 == 32) {
+            if (full1) {
                 // chain length in tiers (8, 16, 32: straight-line code, leading zeros make up the difference)
                 const int c0 = __popc(nz0);
                 const double* top = Z1 + 32 + __popc(nz0 & kb_lanemask_le());
@@ -540,16 +541,6 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
         {
             const uint32_t w = reinterpret_cast<const uint32_t*>(events + 2 * pidx + 1)[lane & 3];  // lane < 4: its write
             const int wcell = __shfl_sync(KB_FULL, nb, (int)(w & 31u));
-#ifdef KB_EXP_WR
-            {
-                const bool wr = lane < n_writes;
-                const int idx = wr ? wcell * spuck + (int)((w >> 5) & 7u) - 1 : 0;
-                const int found = lat[idx], oldsp = (int)((w >> 8) & 15u), newsp = (int)((w >> 12) & 15u);
-                const bool bad = wr && found != oldsp;  // replace_species consistency check (base.mpy:1205)
-                if (bad) status = KB_SPECIES_MISMATCH;
-                if (wr && !bad) lat[idx] = (uint8_t)newsp;
-            }
-#else
             if (lane < n_writes) {
                 const int idx = wcell * spuck + (int)((w >> 5) & 7u) - 1;
                 const int found = lat[idx], oldsp = (int)((w >> 8) & 15u), newsp = (int)((w >> 12) & 15u);
@@ -559,7 +550,6 @@ __global__ void __launch_bounds__(768) kb_smem_kernel(const KbSmemParams prm) {
                     lat[idx] = (uint8_t)newsp;
                 }
             }
-#endif
         }
         // cumulative op counts of the rounds, one byte each; bytes past the last round repeat the total
         unsigned long long ends = ((unsigned long long)eh.z << 32) | eh.y;
