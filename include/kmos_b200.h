@@ -51,7 +51,8 @@ enum {
     KMOS_B200_KERNEL_AUTO = 0,
     KMOS_B200_KERNEL_GENERIC = 1, /* thread-per-replica byte-code engine, state in HBM (all backends) */
     KMOS_B200_KERNEL_SMEM = 2,    /* warp-per-replica, state in shared memory (local_smart that fits) */
-    KMOS_B200_KERNEL_WARP_HBM = 3 /* warp-per-replica, state in HBM/L2 (lat_int: nli_* decision trees per lane) */
+    KMOS_B200_KERNEL_WARP_HBM = 3, /* warp-per-replica, state in HBM/L2 (lat_int: nli_* decision trees per lane) */
+    KMOS_B200_KERNEL_GENERATED = 4 /* exporter-generated per-model CUDA (proclist_<model>.cu), local_smart */
 };
 
 const char *kmos_b200_last_error(void);
@@ -83,6 +84,14 @@ int kmos_b200_select_kernel(kmos_b200_batch *b, int32_t kind);
  * [8]=1 if the avail-site lists stay in HBM/L2, [9]=registers per thread, [10]=1 if split list storage,
  * [11]=bytes of the compact avail image per replica */
 int kmos_b200_kernel_info(kmos_b200_batch *b, int64_t info[12]);
+
+/* Attach the model's generated proclist (proclist_<model>_<hash>.so, written by kmos_b200.codegen next to the
+ * Fortran and compiled with nvcc for sm_100a) to the batch.  replaces: linking the compiled, model-specific
+ * proclist.f90 -- run_proc_nr and its put_/take_ routines (kmos/io/__init__.py:305-465, 2219-2409) -- into
+ * kmc_model (kmos/utils/__init__.py:406-521).  The module must have been generated from the same model blob
+ * (hash checked).  Afterwards KMOS_B200_KERNEL_AUTO prefers KMOS_B200_KERNEL_GENERATED where it fits; the
+ * table interpreter kernels stay available through kmos_b200_select_kernel. */
+int kmos_b200_batch_attach_proclist(kmos_b200_batch *b, const char *so_path);
 
 /* RNG: per-replica Philox4x32-10 stream, key = seed, counter = (kmc_step, replica_id, slot).
  * replaces: random_seed(put=seed_arr) in initialize_state (proclist_generic_subroutines.mpy:253-258).

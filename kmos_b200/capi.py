@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 OK = 0
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SMEM, KERNEL_WARP_HBM = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SMEM, KERNEL_WARP_HBM, KERNEL_GENERATED = 0, 1, 2, 3, 4
 REPLICA_OK, REPLICA_DEADLOCK, REPLICA_SPECIES_MISMATCH, REPLICA_CAPACITY, REPLICA_BAD_MODEL = range(5)
 
 
@@ -26,18 +26,42 @@ class KmosB200Error(RuntimeError):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_otf.cuh", "kb_interp.h", "kb_common.h")] + \
+    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_otf.cuh", "kb_gen.cuh",
+                                            "kb_interp.h", "kb_common.h")] + \
         [os.path.join(os.path.dirname(HERE), "include", "kmos_b200.h")]
+
+
+STAMP = LIB + ".sha256"
+
+
+def source_digest():
+    """Content hash of everything the library is built from (sources + flags): the staleness key."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for s in sources():
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def is_current():
+    """True if the built library matches the sources byte for byte (a checkout that resets mtimes cannot fool it)."""
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() == source_digest()
 
 
 def build(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> kmos_b200/libkmos_b200.so (in-tree)."""
     srcs = sources()
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(s) for s in srcs):
+    if not force and is_current():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, srcs[0]]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, srcs[0], "-ldl"]
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(source_digest() + "\n")
     return LIB
 
 
@@ -70,6 +94,7 @@ def lib():
         "kmos_b200_batch_destroy": (None, [vp]),
         "kmos_b200_batch_volume": (C.c_int, [vp]),
         "kmos_b200_select_kernel": (C.c_int, [vp, i32]),
+        "kmos_b200_batch_attach_proclist": (C.c_int, [vp, C.c_char_p]),
         "kmos_b200_kernel_info": (C.c_int, [vp, arr(np.int64)]),
         "kmos_b200_set_seeds": (C.c_int, [vp, arr(np.uint64), vp]),
         "kmos_b200_set_rates": (C.c_int, [vp, arr(np.float64)]),
@@ -126,7 +151,7 @@ EXPORTED = [
     "kmos_b200_get_avail_sites", "kmos_b200_get_status", "kmos_b200_get_error_info", "kmos_b200_tally_words",
     "kmos_b200_reduce_tallies", "kmos_b200_philox_next", "kmos_b200_batch_set_stream",
     "kmos_b200_measure_smem_bandwidth", "kmos_b200_get_next_kmc_step", "kmos_b200_run_proc_nr",
-    "kmos_b200_reload_replica",
+    "kmos_b200_reload_replica", "kmos_b200_batch_attach_proclist",
 ]
 
 

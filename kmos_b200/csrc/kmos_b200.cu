@@ -24,6 +24,9 @@
 #include "kb_smem.cuh"
 #include "kb_latint.cuh"
 #include "kb_otf.cuh"
+#include "kb_gen.cuh"
+
+#include <dlfcn.h>
 
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
@@ -45,6 +48,15 @@ struct kmos_b200_model {
 };
 
 typedef void (*kb_smem_fn)(const KbSmemParams);
+
+// an exporter-generated proclist module (kmos_b200/codegen.py -> proclist_<model>_<hash>.so), see kb_gen.cuh
+struct KbGenModule {
+    void* handle = nullptr;
+    const KbGenInfo* info = nullptr;
+    int (*plan)(const int32_t*, int32_t, int32_t, KbGenPlan*) = nullptr;
+    int (*build_tables)(const KbGenPlan*, uint32_t*) = nullptr;
+    int (*launch)(const KbGenParams*, int, int, int, void*) = nullptr;
+};
 
 struct kmos_b200_batch {
     kmos_b200_model* model;
@@ -86,6 +98,15 @@ struct kmos_b200_batch {
     KbLatintParams li;
     int li_wpc, li_smem_bytes, li_mode;  // li_mode 0: lat_int decision trees, 1: local_smart flattened ops
     int li_lat_bytes;                    // > 0: bytes per warp of the 4-bit lattice copy in shared memory (else 0)
+    // generated per-model kernel (kmos_b200_batch_attach_proclist)
+    KbGenModule gen;
+    bool gen_ok;
+    KbGenPlan gp;
+    uint32_t* d_gen_tab;
+    uint32_t* d_gen_writes;
+    int32_t* d_gen_dev;        // header + procinfo words for the pack/unpack kernels on the generated kernel's image
+    unsigned char* gen_image;  // [R][gp.img_bytes]
+    int compact_kind;          // which compact image is valid when compact_valid: 0 interpreter, 1 generated
 };
 
 extern "C" const char* kmos_b200_last_error(void) { return g_err.c_str(); }
@@ -535,6 +556,14 @@ static void plan_smem(kmos_b200_batch* b) {
 // 9.4e8 at 24 warps per SM each), so the HBM kernel wins when shared memory can host fewer than about half of
 // the 24 warps it keeps resident itself (ZGB 64x64: 7 warps per SM, 4.7e8 vs 1.06e9).
 static int auto_kernel(const kmos_b200_batch* b) {
+    if (b->gen_ok) {
+        // the generated kernel keeps its lists in L2 like the interpreter's P1G placement, at about half the
+        // instructions per step; the HBM warp kernel wins only when few replicas fit into shared memory
+        double hbm_warps = (double)b->R / (double)(b->sm_count > 0 ? b->sm_count : 1);
+        if (hbm_warps > 24.0) hbm_warps = 24.0;
+        const double gen_score = (double)b->gp.wpc * b->gp.ctas_per_sm;
+        if (!b->li_ok || 0.4 * hbm_warps <= gen_score) return KMOS_B200_KERNEL_GENERATED;
+    }
     if (b->smem_ok && b->li_ok) {
         double hbm_warps = (double)b->R / (double)(b->sm_count > 0 ? b->sm_count : 1);
         if (hbm_warps > 24.0) hbm_warps = 24.0;
@@ -607,6 +636,8 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     plan_smem(b);
     plan_latint(b);
     b->image = nullptr;
+    b->gen_ok = false; b->d_gen_tab = nullptr; b->d_gen_writes = nullptr; b->d_gen_dev = nullptr; b->gen_image = nullptr;
+    b->compact_kind = 0;
     b->compact_valid = false;
     b->d_spec = nullptr;
     b->d_sched = nullptr;
@@ -628,6 +659,8 @@ extern "C" void kmos_b200_batch_destroy(kmos_b200_batch* b) {
     cudaFree(b->d_blob); cudaFree(b->lattice); cudaFree(b->p1); cudaFree(b->p2); cudaFree(b->nsites);
     cudaFree(b->rates); cudaFree(b->integ); cudaFree(b->accum); cudaFree(b->procstat); cudaFree(b->sc);
     cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->occ); cudaFree(b->group_of); cudaFree(b->image); cudaFree(b->d_spec); cudaFree(b->d_sched);
+    cudaFree(b->d_gen_tab); cudaFree(b->d_gen_writes); cudaFree(b->d_gen_dev); cudaFree(b->gen_image);
+    if (b->gen.handle) dlclose(b->gen.handle);
     cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
     cudaStreamDestroy(b->own_stream);
     delete b;
@@ -641,7 +674,10 @@ extern "C" int kmos_b200_select_kernel(kmos_b200_batch* b, int32_t kind) {
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "shared-memory kernel unavailable: " + b->smem_reason);
     if (kind == KMOS_B200_KERNEL_WARP_HBM && !b->li_ok && !b->otf_ok)
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "warp-per-replica HBM kernel unavailable for this model/lattice");
-    if (kind != KMOS_B200_KERNEL_SMEM && kind != KMOS_B200_KERNEL_GENERIC && kind != KMOS_B200_KERNEL_WARP_HBM)
+    if (kind == KMOS_B200_KERNEL_GENERATED && !b->gen_ok)
+        return set_err(KMOS_B200_ERR_UNSUPPORTED, "no generated proclist attached (kmos_b200_batch_attach_proclist)");
+    if (kind != KMOS_B200_KERNEL_SMEM && kind != KMOS_B200_KERNEL_GENERIC && kind != KMOS_B200_KERNEL_WARP_HBM &&
+        kind != KMOS_B200_KERNEL_GENERATED)
         return set_err(KMOS_B200_ERR_ARG, "bad kernel kind");
     b->kernel = kind;
     return KMOS_B200_OK;
@@ -656,6 +692,12 @@ extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[12]) {
         info[7] = (b->R + b->wpc - 1) / b->wpc;
         if (info[7] > (int64_t)b->sm_count * b->ctas_per_sm) info[7] = (int64_t)b->sm_count * b->ctas_per_sm;
         info[8] = b->sp.p1_global; info[9] = b->regs; info[10] = b->sp.split; info[11] = b->sp.img_bytes;
+    } else if (b->kernel == KMOS_B200_KERNEL_GENERATED) {
+        info[1] = b->gp.wpc; info[2] = b->gp.smem_bytes; info[3] = b->gp.ctas_per_sm; info[4] = b->gp.sm_count;
+        info[5] = b->gp.rep_bytes; info[6] = b->gp.tab_bytes;
+        info[7] = (b->R + b->gp.wpc - 1) / b->gp.wpc;
+        if (info[7] > (int64_t)b->gp.sm_count * b->gp.ctas_per_sm) info[7] = (int64_t)b->gp.sm_count * b->gp.ctas_per_sm;
+        info[8] = 1; info[9] = b->gp.regs; info[10] = 0; info[11] = b->gp.img_bytes;
     } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM && b->otf_ok) {
         info[1] = KB_OTF_WARPS; info[2] = KB_OTF_SMEM; info[4] = b->sm_count;
         info[7] = (b->R + KB_OTF_WARPS - 1) / KB_OTF_WARPS; info[8] = 1;
@@ -774,20 +816,35 @@ static KbSmemParams smem_params(const kmos_b200_batch* b) {
 
 // The avail tables live either in the canonical planes p1/p2 (generic engine, getters) or in the compact
 // image (shared-memory engine); convert lazily when the other representation is needed.
+// the generated kernel's image through the same pack/unpack kernels: every process its own upward list
+static KbSmemParams gen_pack_params(const kmos_b200_batch* b) {
+    KbSmemParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.dev = b->d_gen_dev;
+    sp.n_proc = b->model->h.n_proc; sp.ncells = b->g.ncells; sp.cap = b->gp.cap;
+    sp.split = 0; sp.off_hi = b->gp.off_p2; sp.off_p2 = b->gp.off_p2; sp.img_bytes = b->gp.img_bytes;
+    sp.plane_bytes = (int)b->plane_bytes;
+    sp.image = (uint16_t*)b->gen_image; sp.p1 = (uint16_t*)b->p1; sp.p2 = (uint16_t*)b->p2; sp.nsites = b->nsites;
+    sp.R = b->R;
+    return sp;
+}
 static int ensure_canonical(kmos_b200_batch* b) {
     if (!b->compact_valid) return KMOS_B200_OK;
     CU(cudaSetDevice(b->device));
-    kb_unpack_kernel<<<(b->R + 3) / 4, 128, 0, b->stream>>>(smem_params(b));
+    kb_unpack_kernel<<<(b->R + 3) / 4, 128, 0, b->stream>>>(b->compact_kind ? gen_pack_params(b) : smem_params(b));
     CU(cudaGetLastError());
     b->compact_valid = false;
     return KMOS_B200_OK;
 }
-static int ensure_compact(kmos_b200_batch* b) {
-    if (b->compact_valid) return KMOS_B200_OK;
+static int ensure_compact(kmos_b200_batch* b, int kind = 0) {
+    if (b->compact_valid && b->compact_kind == kind) return KMOS_B200_OK;
+    int rc = ensure_canonical(b);
+    if (rc) return rc;
     CU(cudaSetDevice(b->device));
-    kb_pack_kernel<<<(b->R + 3) / 4, 128, 0, b->stream>>>(smem_params(b));
+    kb_pack_kernel<<<(b->R + 3) / 4, 128, 0, b->stream>>>(kind ? gen_pack_params(b) : smem_params(b));
     CU(cudaGetLastError());
     b->compact_valid = true;
+    b->compact_kind = kind;
     return KMOS_B200_OK;
 }
 
@@ -859,6 +916,115 @@ extern "C" int kmos_b200_get_next_kmc_step(kmos_b200_batch* b, int32_t* proc, in
 
 extern "C" int kmos_b200_run_proc_nr(kmos_b200_batch* b, const int32_t* proc, const int32_t* site) {
     return step_io(b, KB_MODE_RUNPROC, const_cast<int32_t*>(proc), const_cast<int32_t*>(site), true, false);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generated per-model kernel: attach a proclist module, launch it
+// ---------------------------------------------------------------------------------------------------
+extern "C" int kmos_b200_batch_attach_proclist(kmos_b200_batch* b, const char* so_path) {
+    if (!b || !so_path) return set_err(KMOS_B200_ERR_ARG, "attach_proclist: bad arguments");
+    if (b->gen_ok) return set_err(KMOS_B200_ERR_ARG, "attach_proclist: a proclist module is already attached");
+    const kmos_b200_model* m = b->model;
+    if (m->h.backend != KB_BACKEND_LOCAL_SMART)
+        return set_err(KMOS_B200_ERR_UNSUPPORTED, "attach_proclist: generated kernels exist for local_smart models");
+    if (b->idx32) return set_err(KMOS_B200_ERR_UNSUPPORTED, "attach_proclist: more than 65535 cells");
+    CU(cudaSetDevice(b->device));
+    KbGenModule g;
+    g.handle = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+    if (!g.handle) return set_err(KMOS_B200_ERR_ARG, std::string("attach_proclist: ") + dlerror());
+    auto info_fn = (const KbGenInfo* (*)(void))dlsym(g.handle, "kmos_b200_gen_info");
+    g.plan = (int (*)(const int32_t*, int32_t, int32_t, KbGenPlan*))dlsym(g.handle, "kmos_b200_gen_plan");
+    g.build_tables = (int (*)(const KbGenPlan*, uint32_t*))dlsym(g.handle, "kmos_b200_gen_build_tables");
+    g.launch = (int (*)(const KbGenParams*, int, int, int, void*))dlsym(g.handle, "kmos_b200_gen_launch");
+    auto fail = [&](int code, const std::string& msg) { dlclose(g.handle); return set_err(code, "attach_proclist: " + msg); };
+    if (!info_fn || !g.plan || !g.build_tables || !g.launch) return fail(KMOS_B200_ERR_ARG, "not a kmos_b200 proclist module");
+    g.info = info_fn();
+    if (g.info->abi != KB_GEN_ABI) return fail(KMOS_B200_ERR_MODEL, "module was generated for another ABI version; regenerate it");
+    const uint64_t h = kb_gen_fnv1a(m->blob.data(), m->blob.size() * 4);
+    if (g.info->model_hash != h || g.info->n_proc != m->h.n_proc || g.info->spuck != m->h.spuck)
+        return fail(KMOS_B200_ERR_MODEL, "module was generated from a different model (table hash mismatch)");
+    if (g.info->n_classes > 32 || g.info->n_proc > 64) return fail(KMOS_B200_ERR_UNSUPPORTED, "class/process count");
+    KbGenPlan gp;
+    const int prc = g.plan(b->g.size, b->R, b->device, &gp);
+    if (prc != 0) {
+        const char* why = prc == -1 ? "lattice has more than 8191 cells" :
+                          prc == -2 ? "lattice smaller than twice the interaction range" :
+                          prc == -4 ? "one replica does not fit in shared memory" : "device query failed";
+        return fail(KMOS_B200_ERR_UNSUPPORTED, why);
+    }
+    const int P = m->h.n_proc;
+    std::vector<uint32_t> tab((size_t)gp.tab_bytes / 4);
+    g.build_tables(&gp, tab.data());
+    std::vector<int32_t> dev(16 + P, 0);
+    dev[9] = 16;
+    for (int q = 0; q < P; ++q)
+        dev[16 + q] = q | (0 << 6) | ((int)g.info->proc_cls[q] << 7) | ((int)g.info->proc_member[q] << 12);
+    uint32_t *d_tab = nullptr, *d_wr = nullptr;
+    int32_t* d_dev = nullptr;
+    unsigned char* img = nullptr;
+    if (cudaMalloc(&d_tab, tab.size() * 4) != cudaSuccess || cudaMalloc(&d_wr, (size_t)P * 16) != cudaSuccess ||
+        cudaMalloc(&d_dev, dev.size() * 4) != cudaSuccess || cudaMalloc(&img, (size_t)b->R * gp.img_bytes) != cudaSuccess ||
+        cudaMemcpy(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_wr, g.info->writes, (size_t)P * 16, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_dev, dev.data(), dev.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d_tab); cudaFree(d_wr); cudaFree(d_dev); cudaFree(img);
+        return fail(KMOS_B200_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!b->d_sched && cudaMalloc(&b->d_sched, ((size_t)b->R + 1) * sizeof(int)) != cudaSuccess) {
+        cudaFree(d_tab); cudaFree(d_wr); cudaFree(d_dev); cudaFree(img);
+        return fail(KMOS_B200_ERR_CUDA, "scheduler counters");
+    }
+    b->gen = g; b->gp = gp; b->d_gen_tab = d_tab; b->d_gen_writes = d_wr; b->d_gen_dev = d_dev; b->gen_image = img;
+    b->gen_ok = true;
+    b->sm_count = gp.sm_count;
+    b->kernel = auto_kernel(b);
+    return KMOS_B200_OK;
+}
+
+static int launch_generated(kmos_b200_batch* b, long long n) {
+    int rc = ensure_compact(b, 1);
+    if (rc) return rc;
+    const KbGenPlan& gp = b->gp;
+    KbGenParams p;
+    memset(&p, 0, sizeof p);
+    p.tab = b->d_gen_tab; p.tab_bytes = gp.tab_bytes; p.nbt_off = gp.nbt_off;
+    p.ncells = gp.ncells; p.cap = gp.cap;
+    p.lattice = b->lattice; p.nsites = b->nsites; p.image = b->gen_image; p.rates = b->rates; p.integ = b->integ;
+    p.procstat = b->procstat; p.sc = b->sc; p.writes = b->d_gen_writes; p.R = b->R; p.nsteps = n;
+    p.rep_bytes = gp.rep_bytes; p.sm_lat = gp.sm_lat; p.sm_ns = gp.sm_ns; p.sm_prod = gp.sm_prod; p.sm_rng = gp.sm_rng;
+    p.sm_mbar = gp.sm_mbar; p.stage_off = gp.stage_off; p.stage_bytes = gp.stage_bytes; p.lat_stride = gp.lat_stride;
+    p.img_bytes = gp.img_bytes;
+    const char* nb = getenv("KMOS_B200_NO_BULK");
+    p.use_bulk = (nb && nb[0] == '1') ? 0 : 1;
+    int wpc = gp.wpc;
+    const char* wenv = getenv("KMOS_B200_WARPS_PER_CTA");
+    if (wenv && atoi(wenv) > 0 && atoi(wenv) <= gp.wpc) wpc = atoi(wenv);
+    const int smem = gp.tab_bytes + wpc * gp.rep_bytes;
+    int blocks = (b->R + wpc - 1) / wpc;
+    const int resident = gp.sm_count * gp.ctas_per_sm;
+    if (blocks > resident) blocks = resident;
+    const long long slots = (long long)blocks * wpc;
+    long long epochs = 1;
+    if (b->R > slots) {
+        epochs = (24 * slots + b->R - 1) / b->R;
+        const long long max_epochs = n / 256 > 0 ? n / 256 : 1;
+        if (epochs > max_epochs) epochs = max_epochs;
+        if (epochs > 64) epochs = 64;
+        if (epochs < 1) epochs = 1;
+    }
+    const char* ep_env = getenv("KMOS_B200_EPOCHS");
+    if (ep_env && atoi(ep_env) > 0) epochs = atoi(ep_env);
+    if ((n + epochs - 1) / epochs > 0x40000000LL) epochs = (n + 0x3fffffffLL) / 0x40000000LL;
+    p.chunk = (n + epochs - 1) / epochs;
+    epochs = (n + p.chunk - 1) / p.chunk;
+    if (epochs * (long long)b->R > 0x7fffffffLL) return set_err(KMOS_B200_ERR_ARG, "do_kmc_steps: too many work items");
+    p.n_items = (int)(epochs * b->R);
+    p.work_counter = b->d_sched;
+    p.done = b->d_sched + 1;
+    CU(cudaMemsetAsync(b->d_sched, 0, ((size_t)b->R + 1) * sizeof(int), b->stream));
+    const int lrc = b->gen.launch(&p, blocks, wpc * 32, smem, (void*)b->stream);
+    if (lrc != 0) return set_err(KMOS_B200_ERR_CUDA, std::string("generated kernel launch: ") + cudaGetErrorString((cudaError_t)lrc));
+    return KMOS_B200_OK;
 }
 
 extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
@@ -938,6 +1104,7 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         CU(cudaGetLastError());
         return KMOS_B200_OK;
     }
+    if (b->kernel == KMOS_B200_KERNEL_GENERATED) return launch_generated(b, n);
     int rc = ensure_compact(b);
     if (rc) return rc;
     KbSmemParams sp = smem_params(b);

@@ -47,7 +47,9 @@ class Model(object):
 
 class Batch(object):
     def __init__(self, model, n_replicas, size, device=0, seeds=None, replica_ids=None, rates=None, lut=None,
-                 kernel=capi.KERNEL_AUTO, init=True, layer=None):
+                 kernel=capi.KERNEL_AUTO, init=True, layer=None, proclist=None):
+        """proclist: path of the model's generated proclist module (kmos_b200.codegen.build), "auto" to use the
+        cached build of this model if there is one, "build" to generate + compile it now, or None."""
         self.L = capi.lib()
         self.model = model
         self.R = int(n_replicas)
@@ -62,6 +64,9 @@ class Batch(object):
         self.volume = self.L.kmos_b200_batch_volume(h)
         self.ncells = self.volume // model.spuck
         self.layer = model.default_layer if layer is None else int(layer)
+        self.proclist = None
+        if proclist:
+            self.attach_proclist(proclist)
         if kernel != capi.KERNEL_AUTO:
             self.select_kernel(kernel)
         self.set_seeds(np.arange(self.R, dtype=np.uint64) if seeds is None else seeds, replica_ids)
@@ -73,6 +78,25 @@ class Batch(object):
             self.init_state()
 
     # ---- setup -----------------------------------------------------------------------------------------
+    def attach_proclist(self, proclist="auto"):
+        """Attach the model's exporter-generated CUDA proclist (kmos_b200_batch_attach_proclist).  Returns the
+        module path, or None when "auto" finds no cached build or the generator declines the model."""
+        from . import codegen, devtables
+        path = proclist
+        if proclist in ("auto", "build"):
+            try:
+                if proclist == "build":
+                    path = codegen.build(self.model.ir, self.model.blob)
+                else:
+                    path = codegen.find_built(self.model.ir, self.model.blob)
+            except devtables.Unsupported:
+                path = None
+            if path is None:
+                return None
+        capi.check(self.L.kmos_b200_batch_attach_proclist(self.h, str(path).encode()))
+        self.proclist = path
+        return path
+
     def select_kernel(self, kind):
         capi.check(self.L.kmos_b200_select_kernel(self.h, int(kind)))
 
@@ -84,7 +108,7 @@ class Batch(object):
                 "image_bytes_per_replica")
         d = dict(zip(keys, (int(x) for x in info)))
         d["kernel_name"] = {capi.KERNEL_GENERIC: "generic", capi.KERNEL_SMEM: "smem",
-                            capi.KERNEL_WARP_HBM: "warp_hbm"}[d["kernel"]]
+                            capi.KERNEL_WARP_HBM: "warp_hbm", capi.KERNEL_GENERATED: "generated"}[d["kernel"]]
         return d
 
     def set_seeds(self, seeds, replica_ids=None):
