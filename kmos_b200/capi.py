@@ -75,6 +75,13 @@ def lib():
     if not os.path.exists(LIB):
         raise KmosB200Error("%s not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(there is no CPU fallback)" % LIB)
+    if not is_current():
+        # a library older than its sources is never used silently: rebuild it, or say so
+        import shutil
+        if shutil.which(os.environ.get("NVCC", "nvcc")):
+            build()
+        else:
+            raise KmosB200Error("%s does not match its sources and there is no nvcc to rebuild it" % LIB)
     L = C.CDLL(LIB)
     vp, i32, i64, u32, u64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
 

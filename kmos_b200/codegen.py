@@ -19,7 +19,7 @@ The result is compiled with nvcc for sm_100a into ``proclist_<model>_<hash>.so``
 attached to a batch with ``kmos_b200_batch_attach_proclist``; the table interpreter (kb_smem.cuh) stays the
 path for models this generator declines (``Unsupported``).
 
-    python -m kmos_b200.codegen <model_tables.json | export_dir> [-o out_dir] [--build]
+    python -m kmos_b200.codegen <model_tables.json | export_dir> [-o out_dir] [--style unrolled|compact] [--build]
 """
 import hashlib
 import os
@@ -34,10 +34,10 @@ from .devtables import KIND_ADD, Unsupported
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 CACHE = os.path.join(HERE, "_proclist_cache")
-GEN_VERSION = 2
+GEN_VERSION = 3
 MAX_COND = 4
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
 
 
 def fnv1a(data):
@@ -114,46 +114,69 @@ def analyse(ir):
             "dim": ir["model_dimension"], "species": ir["species"]}
 
 
-def _qw(nc):
-    return 0 if nc == 0 else (1 + 3 * nc + 3) // 4
+KINDS = {(True, False): "del", (False, True): "add", (True, True): "mixed"}
+# estimated SASS instructions of a round body; the event code of the unrolled style must stay inside the SM's
+# instruction cache next to the ~700 instructions of the step skeleton (measured: mini_101 and AB profit from
+# unrolling, RuO2's 12 k instructions thrash the cache -- DESIGN.md 4.1b)
+UNROLL_BUDGET = 1600
+
+
+def _round_cost(has_del, has_add, nc):
+    return (60 if has_del and has_add else 40 if has_add else 35) + 7 * nc
 
 
 def layout(an):
-    """Place every round's operand arrays: region A (one uint4 per op, all rounds), then one region per probe
-    count with equally sized entries -- idle lanes of a round read on into entries of the same format."""
-    a_off = 0
+    """Number the ops and rounds in table order and place the table's regions:
+    [A: one uint4 per op][B: bw probe words per op][round words][event rows].  Idle lanes of a round read up
+    to 31 entries past its last op, hence the padding behind A and B."""
     rounds = []
+    first = 0
+    ncmax = 0
     for e, ev in enumerate(an["events"]):
         for r, rnd in enumerate(ev["rounds"]):
+            if len(rnd) > 32:
+                raise Unsupported("a round with more than 32 ops")
             nc = max(len(op[3]) for op in rnd)
-            rounds.append({"event": e, "round": r, "count": len(rnd), "nc": nc, "a_off": a_off,
+            ncmax = max(ncmax, nc)
+            rounds.append({"event": e, "round": r, "count": len(rnd), "nc": nc, "first_op": first,
                            "has_add": any(op[0] == KIND_ADD for op in rnd),
                            "has_del": any(op[0] != KIND_ADD for op in rnd)})
-            a_off += 16 * len(rnd)
-    pos = a_off + 512
-    for qw in range(0, _qw(MAX_COND) + 1):
-        stride = 4 if qw == 0 else 16 * qw
-        used = False
-        for rd in rounds:
-            if _qw(rd["nc"]) == qw:
-                rd["b_off"] = pos
-                pos += stride * rd["count"]
-                used = True
-        if used:
-            pos = (pos + 32 * stride + 15) // 16 * 16
-    first = 0
+            first += len(rnd)
+    n_ops = first
+    if n_ops + 32 > 0xffff:
+        raise Unsupported("more than 65503 list operations")
+    if len(rounds) > 0 and max(len(ev["rounds"]) for ev in an["events"]) > 255:
+        raise Unsupported("more than 255 rounds in one event")
+    bw = {0: 0, 1: 1, 2: 2, 3: 4, 4: 4}[ncmax]
+    off_b = 16 * (n_ops + 32)
+    off_rd = (off_b + 4 * bw * (n_ops + 32) + 15) // 16 * 16
+    off_ev = (off_rd + 4 * (len(rounds) + 1) + 15) // 16 * 16
+    ops_bytes = (off_ev + 24 * an["nproc"] + 15) // 16 * 16
+    # round bodies the model uses, the statically most frequent first
+    variants = {}
     for rd in rounds:
-        rd["first_op"] = first
-        first += rd["count"]
-    return rounds, pos
+        key = (rd["has_del"], rd["has_add"], rd["nc"])
+        variants[key] = variants.get(key, 0) + 1
+    order = sorted(variants, key=lambda k: -variants[k])
+    for rd in rounds:
+        rd["kind"] = order.index((rd["has_del"], rd["has_add"], rd["nc"]))
+    cost = sum(_round_cost(rd["has_del"], rd["has_add"], rd["nc"]) for rd in rounds) + 25 * an["nproc"]
+    return {"rounds": rounds, "n_ops": n_ops, "bw": bw, "off_b": off_b, "off_rd": off_rd, "off_ev": off_ev,
+            "ops_bytes": ops_bytes, "variants": order, "unrolled_cost": cost}
 
 
-def generate(ir, blob=None, name=None, max_threads=768):
-    """-> (CUDA source text, info dict) for a local_smart model IR."""
+def generate(ir, blob=None, name=None, max_threads=768, style="auto"):
+    """-> (CUDA source text, info dict) for a local_smart model IR.  style: "unrolled" (every process its own
+    straight-line case), "compact" (events as descriptor rows over the model's round bodies) or "auto"."""
     if blob is None:
         blob, _info = tables.build_blob(ir)
     an = analyse(ir)
-    rounds, ops_bytes = layout(an)
+    lay = layout(an)
+    rounds = lay["rounds"]
+    if style == "auto":
+        style = os.environ.get("KMOS_B200_GEN_STYLE") or ("unrolled" if lay["unrolled_cost"] <= UNROLL_BUDGET else "compact")
+    if style not in ("unrolled", "compact"):
+        raise ValueError("style: unrolled, compact or auto")
     fx = ir.get("fixture")
     name = name or ir.get("model_name") or (fx.get("model") if isinstance(fx, dict) else fx) or "model"
     ident = "".join(ch if ch.isalnum() else "_" for ch in name)
@@ -161,7 +184,8 @@ def generate(ir, blob=None, name=None, max_threads=768):
     P = an["nproc"]
     out = []
     w = out.append
-    w("// proclist_%s.cu -- generated by kmos_b200.codegen (version %d); do not edit." % (ident, GEN_VERSION))
+    w("// proclist_%s.cu -- generated by kmos_b200.codegen (version %d, %s style); do not edit." % (
+        ident, GEN_VERSION, style))
     w("// CUDA twin of the proclist.f90 `kmos export -b local_smart` writes for this model: run_proc_nr as a switch,")
     w("// every process' replace_species calls and guarded del_proc / if-tree add_proc calls as straight-line code")
     w("// (kmos/io/__init__.py:305-465, 2219-2409, 2568-2655).  model blob hash %016x" % h)
@@ -171,47 +195,81 @@ def generate(ir, blob=None, name=None, max_threads=768):
     w("struct KbModel {")
     w("    static constexpr int P = %d, SPUCK = %d, NOFF = %d, MAX_THREADS = %d;" % (
         P, an["spuck"], len(an["offsets"]), max_threads))
+    w("    static constexpr int BW = %d, OFF_B = %d, OFF_EV = %d;  // operand table layout" % (
+        lay["bw"], lay["off_b"], lay["off_ev"]))
     w("    typedef KbGenCtx<KbModel> Ctx;")
     by_event = {}
     for rd in rounds:
         by_event.setdefault(rd["event"], []).append(rd)
-    for e, ev in enumerate(an["events"]):
+
+    def describe(e, ev):
         w("")
         w("    // process %d: %s" % (e + 1, ev["name"]))
-        for i, (off, n, old, new) in enumerate(ev["writes"]):
+        for off, n, old, new in ev["writes"]:
             w("    //   replace_species(site + (%d,%d,%d) type %d, %s -> %s)" % (
                 an["offsets"][off] + (n, an["species"][old], an["species"][new])))
-        w("    static __device__ __forceinline__ void ev_%d(Ctx& c, const int k) {" % (e + 1))
-        w("        c.select<%d>(k);" % e)
-        for i, (off, n, old, new) in enumerate(ev["writes"]):
-            w("        c.write<%d, %d, %d, %d, %d>();" % (i, off, n, old, new))
-        rds = by_event.get(e, [])
 
-        def load(j):
-            rd = rds[j]
-            w("        const uint4 a%d = c.ldA<%d>(); const KbGenOpB b%d = c.ldB<%d, %d>();" % (
-                j, rd["a_off"], j, rd["b_off"], rd["nc"]))
+    def ops_text(ops):
+        return " ".join(("+" if op[0] == KIND_ADD else "-") + str(op[1]) for op in ops)
 
-        if rds:
-            load(0)
-        for j, rd in enumerate(rds):
-            if j + 1 < len(rds):
-                load(j + 1)
-            ops = ev["rounds"][j]
-            w("        c.round<%d, %s, %s, %d>(a%d, b%d);  // %s" % (
-                rd["count"], "true" if rd["has_del"] else "false", "true" if rd["has_add"] else "false", rd["nc"],
-                j, j, " ".join(("+" if op[0] == KIND_ADD else "-") + str(op[1]) for op in ops)))
-        if not rds:
-            w("        __syncwarp();")
+    if style == "unrolled":
+        for e, ev in enumerate(an["events"]):
+            describe(e, ev)
+            w("    static __device__ __forceinline__ void ev_%d(Ctx& c, const int k) {" % (e + 1))
+            w("        c.select<%d>(k);" % e)
+            for i, (off, n, old, new) in enumerate(ev["writes"]):
+                w("        c.write<%d, %d, %d, %d, %d>();" % (i, off, n, old, new))
+            rds = by_event.get(e, [])
+
+            def load(j):
+                w("        const uint4 a%d = c.ldA(%d); const KbGenOpB b%d = c.ldB(%d);" % (
+                    j, rds[j]["first_op"], j, rds[j]["first_op"]))
+
+            if rds:
+                load(0)
+            for j, rd in enumerate(rds):
+                if j + 1 < len(rds):
+                    load(j + 1)
+                w("        c.round<%s, %s, %d>(%d, a%d, b%d);  // %s" % (
+                    "true" if rd["has_del"] else "false", "true" if rd["has_add"] else "false", rd["nc"],
+                    rd["count"], j, j, ops_text(ev["rounds"][j])))
+            if not rds:
+                w("        __syncwarp();")
+            w("    }")
+        w("")
+        w("    static __device__ __forceinline__ void run_event(Ctx& c, const int pidx, const int k) {")
+        w("        switch (pidx) {")
+        for e in range(P):
+            w("        case %d: ev_%d(c, k); break;" % (e, e + 1))
+        w("        default: break;")
+        w("        }")
         w("    }")
-    w("")
-    w("    static __device__ __forceinline__ void run_event(Ctx& c, const int pidx, const int k) {")
-    w("        switch (pidx) {")
-    for e in range(P):
-        w("        case %d: ev_%d(c, k); break;" % (e, e + 1))
-    w("        default: break;")
-    w("        }")
-    w("    }")
+    else:
+        for e, ev in enumerate(an["events"]):
+            describe(e, ev)
+            for j, rd in enumerate(by_event.get(e, [])):
+                w("    //   round %d (%s, %d probes): %s" % (
+                    j, KINDS[(rd["has_del"], rd["has_add"])], rd["nc"], ops_text(ev["rounds"][j])))
+        w("")
+        w("    // the round bodies this model uses; kind = position in this switch")
+        w("    static __device__ __forceinline__ void dispatch(Ctx& c, const uint32_t kind, const int count,")
+        w("                                                    const uint4 a, const KbGenOpB& b) {")
+        if len(lay["variants"]) <= 1:
+            for hd, ha, nc in lay["variants"]:
+                w("        c.round<%s, %s, %d>(count, a, b);" % ("true" if hd else "false", "true" if ha else "false", nc))
+            if not lay["variants"]:
+                w("        __syncwarp();")
+        else:
+            w("        switch (kind) {")
+            for i, (hd, ha, nc) in enumerate(lay["variants"]):
+                w("        %s c.round<%s, %s, %d>(count, a, b); break;  // %s" % (
+                    "default:" if i == len(lay["variants"]) - 1 else "case %d:" % i,
+                    "true" if hd else "false", "true" if ha else "false", nc, KINDS[(hd, ha)]))
+            w("        }")
+        w("    }")
+        w("    static __device__ __forceinline__ void run_event(Ctx& c, const int pidx, const int k) {")
+        w("        kb_gen_run_compact<KbModel>(c, pidx, k);")
+        w("    }")
     w("};")
     w("")
     w("const KbGenOpDesc kb_ops[] = {")
@@ -226,14 +284,21 @@ def generate(ir, blob=None, name=None, max_threads=768):
                     1 if kind == KIND_ADD else 0, q - 1, an["cls_of"][q], an["member_of"][q], aoff, len(cs),
                     ",".join(map(str, co)), ",".join(map(str, cn)), ",".join(map(str, cm))))
                 n_ops += 1
+    assert n_ops == lay["n_ops"]
     if n_ops == 0:
         w("    {0, 0, 0, 0, 0, 0, {0,0,0,0}, {0,0,0,0}, {0,0,0,0}},")
     w("};")
     w("const KbGenRoundDesc kb_rounds[] = {")
     for rd in rounds:
-        w("    {%d, %d, %d, %d, %d}," % (rd["first_op"], rd["count"], rd["nc"], rd["a_off"], rd["b_off"]))
+        w("    {%d, %d, %d, %d}," % (rd["first_op"], rd["count"], rd["nc"], rd["kind"]))
     if not rounds:
-        w("    {0, 0, 0, 0, 0},")
+        w("    {0, 0, 0, 0},")
+    w("};")
+    w("const KbGenEventDesc kb_events[] = {")
+    fr = 0
+    for ev in an["events"]:
+        w("    {%d, %d}," % (fr, len(ev["rounds"])))
+        fr += len(ev["rounds"])
     w("};")
     w("const int8_t kb_offsets[] = {%s};" % ", ".join("%d,%d,%d" % o for o in an["offsets"]))
     w("const uint32_t kb_writes[] = {")
@@ -244,23 +309,26 @@ def generate(ir, blob=None, name=None, max_threads=768):
     w("};")
     w("const uint8_t kb_proc_cls[] = {%s};" % ", ".join(str(an["cls_of"][q]) for q in range(1, P + 1)))
     w("const uint8_t kb_proc_member[] = {%s};" % ", ".join(str(an["member_of"][q]) for q in range(1, P + 1)))
-    w("const KbGenInfo kb_info = {KB_GEN_ABI, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, 0x%016xull, \"%s\"," % (
-        P, an["n_species"], an["spuck"], an["dim"], len(an["offsets"]), len(an["classes"]), n_ops, len(rounds),
-        ops_bytes, max_threads, h, ident))
-    w("                           kb_ops, kb_rounds, kb_offsets, kb_writes, kb_proc_cls, kb_proc_member};")
+    w("const KbGenInfo kb_info = {KB_GEN_ABI, %d, %d, %d, %d, %d, %d, %d, %d," % (
+        P, an["n_species"], an["spuck"], an["dim"], len(an["offsets"]), len(an["classes"]), n_ops, len(rounds)))
+    w("                           %d, %d, %d, %d, %d, %d, %d, 0x%016xull, \"%s\"," % (
+        lay["bw"], lay["off_b"], lay["off_rd"], lay["off_ev"], lay["ops_bytes"], max_threads,
+        1 if style == "compact" else 0, h, ident))
+    w("                           kb_ops, kb_rounds, kb_events, kb_offsets, kb_writes, kb_proc_cls, kb_proc_member};")
     w("}  // namespace")
     w("")
     w("KB_GEN_MODULE(KbModel, kb_info)")
     w("")
-    info = {"name": ident, "hash": h, "n_ops": n_ops, "n_rounds": len(rounds), "ops_bytes": ops_bytes,
-            "n_classes": len(an["classes"]), "n_offsets": len(an["offsets"]),
+    info = {"name": ident, "hash": h, "n_ops": n_ops, "n_rounds": len(rounds), "ops_bytes": lay["ops_bytes"],
+            "n_classes": len(an["classes"]), "n_offsets": len(an["offsets"]), "style": style,
+            "unrolled_cost": lay["unrolled_cost"], "variants": lay["variants"],
             "rounds_per_event": [len(ev["rounds"]) for ev in an["events"]]}
     return "\n".join(out), info
 
 
-def write_source(ir, out_dir, blob=None, name=None, max_threads=768):
+def write_source(ir, out_dir, blob=None, name=None, max_threads=768, style="auto"):
     """Write proclist_<model>.cu into `out_dir` (next to the exported Fortran); returns its path."""
-    src, info = generate(ir, blob, name, max_threads)
+    src, info = generate(ir, blob, name, max_threads, style)
     path = os.path.join(out_dir, "proclist_%s.cu" % info["name"])
     with open(path, "w") as f:
         f.write(src)
@@ -275,11 +343,11 @@ def _skeleton_digest():
     return hsh
 
 
-def build(ir, blob=None, name=None, out_dir=None, max_threads=768, verbose=False):
+def build(ir, blob=None, name=None, out_dir=None, max_threads=768, verbose=False, style="auto"):
     """Generate and compile; the shared object is cached under the content hash of source + skeleton.
 
     -> path of proclist_<model>_<hash>.so"""
-    src, info = generate(ir, blob, name, max_threads)
+    src, info = generate(ir, blob, name, max_threads, style)
     hsh = _skeleton_digest()
     hsh.update(src.encode())
     hsh.update(" ".join(NVCC_FLAGS).encode())
@@ -299,9 +367,9 @@ def build(ir, blob=None, name=None, out_dir=None, max_threads=768, verbose=False
     return so
 
 
-def find_built(ir, blob=None, name=None, out_dir=None, max_threads=768):
+def find_built(ir, blob=None, name=None, out_dir=None, max_threads=768, style="auto"):
     """Path of the cached shared object for this model, or None (no compiler is invoked)."""
-    src, info = generate(ir, blob, name, max_threads)
+    src, info = generate(ir, blob, name, max_threads, style)
     hsh = _skeleton_digest()
     hsh.update(src.encode())
     hsh.update(" ".join(NVCC_FLAGS).encode())
@@ -312,6 +380,10 @@ def find_built(ir, blob=None, name=None, out_dir=None, max_threads=768):
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("-")]
     do_build = "--build" in sys.argv
+    style = "auto"
+    if "--style" in sys.argv:
+        style = sys.argv[sys.argv.index("--style") + 1]
+        args = [a for a in args if a != style]
     out = None
     if "-o" in sys.argv:
         out = sys.argv[sys.argv.index("-o") + 1]
@@ -321,7 +393,8 @@ if __name__ == "__main__":
         src_path = os.path.join(src_path, "model_tables.json")
     model_ir = tables.load_ir(src_path)
     out = out or os.path.dirname(os.path.abspath(src_path))
-    path, inf = write_source(model_ir, out)
-    print("%s: %d ops in %d rounds, %d table bytes" % (path, inf["n_ops"], inf["n_rounds"], inf["ops_bytes"]))
+    path, inf = write_source(model_ir, out, style=style)
+    print("%s: %s style, %d ops in %d rounds, %d table bytes" % (path, inf["style"], inf["n_ops"], inf["n_rounds"],
+                                                             inf["ops_bytes"]))
     if do_build:
-        print(build(model_ir, verbose=True))
+        print(build(model_ir, verbose=True, style=style))

@@ -19,9 +19,18 @@
 // One warp steps one replica.  Plane 2 of avail_sites (one uint16 entry per exclusivity class and cell, see
 // kmos_b200/devtables.py) and the lattice stay in shared memory for the whole work item; plane 1 (one list per
 // process, always growing upwards) stays in HBM/L2.  The CTA's warps share the model's operand table: per
-// round one uint4 per op with ready-made byte offsets (neighbour-table column, class plane, nr_of_sites entry,
-// list base) plus the member tag / probe words, specialised on the host for the lattice geometry
-// (kb_gen_build_tables) -- the device code never decodes a field.
+// op one uint4 with ready-made byte offsets (neighbour-table column, class plane, 4 * process) and the member
+// tag, plus one packed word per if-tree probe, specialised on the host for the lattice geometry
+// (kb_gen_build_tables).
+//
+// Two code styles, chosen by the generator from the size of the model's event code:
+//   unrolled  every process is its own straight-line case (what kmos does in Fortran).  Fastest while the
+//             whole kernel stays inside the SM's instruction cache (mini_101, AB: 2-3 k SASS instructions).
+//   compact   RuO2's 36 cases unroll to 12 k instructions = 196 KB of SASS; with 22 warps of a CTA in
+//             different cases the instruction cache thrashes (ncu r2: 6.5 cycles of no_instruction stall per
+//             issued instruction, IPC 1.3).  Here the generator emits only the round bodies the model uses
+//             (dispatch() = a switch over its (del, add, probes) variants) and the events become rows of a
+//             descriptor table: writes and rounds are read, not decoded field by field.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,7 +38,7 @@
 
 #include "kb_smem.cuh"
 
-#define KB_GEN_ABI 2
+#define KB_GEN_ABI 3
 #define KB_GEN_MAX_COND 4
 #define KB_GEN_KIND_ADD 0x80000000u
 #define KB_GEN_TABLE_PAD 1024  // idle lanes of a round read up to 32 entries past its last op
@@ -40,15 +49,21 @@ struct KbGenOpDesc {  // one list operation, in table order
     uint8_t coff[KB_GEN_MAX_COND], cn[KB_GEN_MAX_COND];
     uint16_t cmask[KB_GEN_MAX_COND];
 };
-struct KbGenRoundDesc {  // operands of one round: `count` ops from `first_op`
-    int32_t first_op, count, nc, a_off, b_off;  // byte offsets of the two operand arrays inside the table
+struct KbGenRoundDesc {  // one round: `count` ops from `first_op`, at most `nc` probes each
+    int32_t first_op, count, nc, kind;  // kind: index of the round body in the model's dispatch()
+};
+struct KbGenEventDesc {  // one process: its rounds
+    int32_t first_round, n_rounds;
 };
 struct KbGenInfo {
-    int32_t abi, n_proc, n_species, spuck, dim, n_off, n_classes, n_ops, n_rounds, ops_bytes, max_threads;
+    int32_t abi, n_proc, n_species, spuck, dim, n_off, n_classes, n_ops, n_rounds;
+    // operand table: [A: uint4 per op][B: bw probe words per op][round words][event rows][neighbour table]
+    int32_t bw, off_b, off_rd, off_ev, ops_bytes, max_threads, compact;
     uint64_t model_hash;  // FNV-1a of the int32 model blob the code was generated from
     const char* name;
     const KbGenOpDesc* ops;
     const KbGenRoundDesc* rounds;
+    const KbGenEventDesc* events;
     const int8_t* offsets;     // [n_off][3]
     const uint32_t* writes;    // [n_proc][4]: off_id | n<<8 | old<<16 | new<<24, 0 = none (error reporting)
     const uint8_t* proc_cls;   // [n_proc] exclusivity class
@@ -112,9 +127,14 @@ __device__ __forceinline__ uint32_t kb_shr(uint32_t x, uint32_t s) {  // shift a
     return v;
 }
 
-struct KbGenOpB {  // member tag | kind, then up to 4 probes (column, site, species mask)
-    uint32_t k;
-    uint32_t c[3 * KB_GEN_MAX_COND];
+__device__ __forceinline__ uint2 kb_ldc64(uint32_t a) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
+struct KbGenOpB {  // up to 4 if-tree probes: column (byte 0), site (byte 1), species mask (high half)
+    uint32_t c[KB_GEN_MAX_COND];
 };
 
 // the replica's mutable shared-memory state (class planes, nr_of_sites, lattice) by 32-bit shared address
@@ -141,14 +161,16 @@ __device__ __forceinline__ void kb_sts8(uint32_t a, uint32_t v) { asm volatile("
 template <class M>
 struct KbGenCtx {
     uint32_t wb;         // shared address of this warp's block: class planes at 0
+    uint32_t wns;        // ... of its nr_of_sites array
     uint32_t lat;        // ... of its lattice copy
     unsigned char* p1;   // the replica's lists in HBM/L2 (list of process q at byte q*cap*2)
     uint32_t tab0;       // shared address of the operand table
-    uint32_t tabA;       // ... + lane*16
-    uint32_t tabK;       // ... + lane*4
+    uint32_t tabA;       // ... + lane*16: this lane's uint4 of a round whose first op sits at offset 0
+    uint32_t tabB;       // ... + OFF_B + lane*4*BW: this lane's probe words
     uint32_t nbT;        // shared address of the neighbour table: row = cell, column = offset, value = 2*cell'
     uint32_t nbrow;      // row of the selected cell
     int lane, C, cap;
+    uint32_t capH;       // cap / 2: list byte offset of process q = (4*q) * capH
     uint32_t cell2;      // 2 * selected cell
     uint32_t bad;        // bit 0: capacity, bit 1+i: write i found another species
     uint32_t cntA, cntB; // events of this lane's processes in the current work item
@@ -172,6 +194,18 @@ struct KbGenCtx {
         cell2 = 2u * cell;
         nbrow = nbT + cell * (2 * M::NOFF);
     }
+    __device__ __forceinline__ void select_rt(const int q, const int k) {  // the same, process number in a register
+        const uint32_t cell = *list_at(2u * (uint32_t)(q * cap + k - 1));
+        if (M::P > 32) {
+            const uint32_t hit = lane == (q >> 1);
+            cntB += hit & (uint32_t)q;
+            cntA += hit & ~(uint32_t)q;
+        } else {
+            cntA += (lane == q);
+        }
+        cell2 = 2u * cell;
+        nbrow = nbT + cell * (2 * M::NOFF);
+    }
     __device__ __forceinline__ uint32_t lat_index(uint32_t c2) const {
         return (M::SPUCK % 2 == 0) ? c2 * (M::SPUCK / 2) : (c2 * M::SPUCK) >> 1;
     }
@@ -183,58 +217,62 @@ struct KbGenCtx {
         if (kb_lds8(p) == OLD) kb_sts8(p, NEW);
         else bad |= 2u << I;
     }
-    template <int OFF>
-    __device__ __forceinline__ uint4 ldA() const { return kb_ldc128(tabA + OFF); }
-    template <int OFF, int NC>
-    __device__ __forceinline__ KbGenOpB ldB() const {
+    // the same from an event row: w = column | (site - 1) << 8 | old << 16 | new << 24
+    __device__ __forceinline__ void write_rt(const int i, const uint32_t w) {
+        const uint32_t c2 = kb_ldc16(nbrow + (w & 0xffu));
+        const uint32_t p = lat + lat_index(c2) + ((w >> 8) & 0xffu);
+        if (kb_lds8(p) == ((w >> 16) & 0xffu)) kb_sts8(p, w >> 24);
+        else bad |= 2u << i;
+    }
+    // operands of the round whose first op has index I (lane l: op I + l)
+    __device__ __forceinline__ uint4 ldA(const uint32_t i) const { return kb_ldc128(tabA + 16u * i); }
+    __device__ __forceinline__ KbGenOpB ldB(const uint32_t i) const {
         KbGenOpB b;
-        if (NC == 0) {
-            b.k = kb_ldc32(tabK + OFF);
-        } else {
-            constexpr int QW = (1 + 3 * NC + 3) / 4;  // uint4 per op
-            const uint32_t base = (QW == 1 ? tabA : tab0 + (uint32_t)lane * (16u * QW)) + OFF;
-            uint32_t w[4 * QW];
-#pragma unroll
-            for (int i = 0; i < QW; ++i) {
-                const uint4 v = kb_ldc128(base + 16 * i);
-                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-            }
-            b.k = w[0];
-#pragma unroll
-            for (int i = 0; i < 3 * NC; ++i) b.c[i] = w[1 + i];
+        b.c[0] = b.c[1] = b.c[2] = b.c[3] = 0;
+        if (M::BW == 1) {
+            b.c[0] = kb_ldc32(tabB + 4u * i);
+        } else if (M::BW == 2) {
+            const uint2 v = kb_ldc64(tabB + 8u * i);
+            b.c[0] = v.x; b.c[1] = v.y;
+        } else if (M::BW == 4) {
+            const uint4 v = kb_ldc128(tabB + 16u * i);
+            b.c[0] = v.x; b.c[1] = v.y; b.c[2] = v.z; b.c[3] = v.w;
         }
         return b;
     }
 
-    // One round: lane l < COUNT executes op l of the round.  a = (neighbour column, class plane, nr_of_sites
-    // entry, list base), all byte offsets; b.k = member << 13 | (add ? 1 << 31 : 0).
+    // One round: lane l < count executes op l of the round.  a = (neighbour column, class plane, 4 * process,
+    // member << 13 | (add ? 1 << 31 : 0)), the first two as byte offsets.
     //   guarded del_proc (base.mpy:211-265): registered iff the class entry carries this op's member tag
     //   add_proc (base.mpy:268-302) after the if-tree probes of its leaf (io/__init__.py:2568-2655)
-    template <int COUNT, bool HAS_DEL, bool HAS_ADD, int NC>
-    __device__ __forceinline__ void round(const uint4 a, const KbGenOpB& b) {
-        const bool valid = COUNT >= 32 || lane < COUNT;
+    template <bool HAS_DEL, bool HAS_ADD, int NC>
+    __device__ __forceinline__ void round(const int count, const uint4 a, const KbGenOpB& b) {
+        const bool valid = lane < count;
         const uint32_t ca2 = kb_ldc16(nbrow + a.x);
         bool ok = valid;
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-            const uint32_t cc2 = kb_ldc16(nbrow + b.c[3 * j]);
-            const uint32_t sp = kb_lds8(lat + b.c[3 * j + 1] + lat_index(cc2));
-            ok = ok && (kb_shr(b.c[3 * j + 2], sp) & 1u);
+            const uint32_t w = b.c[j];
+            const uint32_t cc2 = kb_ldc16(nbrow + (w & 0xffu));
+            const uint32_t sp = kb_lds8(lat + ((w >> 8) & 0xffu) + lat_index(cc2));
+            ok = ok && (kb_shr(w, 16u + sp) & 1u);
         }
-        const uint32_t nsa = wb + a.z;
+        const uint32_t nsa = wns + a.z;
         const int nq = (int)kb_lds32(nsa);
         const uint32_t plane = wb + a.y;
         const uint32_t ea = plane + ca2;
         const uint32_t e = kb_lds16(ea);
-        const bool is_add = HAS_ADD && (!HAS_DEL || (int)b.k < 0);
+        const uint32_t lb = a.z * capH;  // byte offset of the process' list
+        const uint32_t kk = a.w;
+        const bool is_add = HAS_ADD && (!HAS_DEL || (int)kk < 0);
         if (HAS_DEL && !HAS_ADD) {
-            const uint32_t t = (e ^ b.k) & 0xffffu;  // < 0x2000: registered, and t is its position
+            const uint32_t t = (e ^ kk) & 0xffffu;  // < 0x2000: registered, and t is its position
             const bool go = valid && t < 0x2000u;
             // the element a del would move, requested before anything depends on it
-            const uint32_t last = *list_at(a.w + 2u * (uint32_t)((valid && nq > 0) ? nq - 1 : 0));
+            const uint32_t last = *list_at(lb + 2u * (uint32_t)((valid && nq > 0) ? nq - 1 : 0));
             if (go) {
                 if ((int)t < nq) {
-                    *list_at(a.w + 2u * (t - 1u)) = (uint16_t)last;
+                    *list_at(lb + 2u * (t - 1u)) = (uint16_t)last;
                     kb_sts16(plane + 2u * last, e);
                 }
                 kb_sts16(ea, 0u);
@@ -244,29 +282,60 @@ struct KbGenCtx {
             const bool go = ok && e == 0 && nq < C;
             if (ok && !go) bad |= 1u;
             if (go) {
-                *list_at(a.w + 2u * (uint32_t)nq) = (uint16_t)(ca2 >> 1);
-                kb_sts16(ea, (b.k & 0xffffu) | (uint32_t)(nq + 1));
+                *list_at(lb + 2u * (uint32_t)nq) = (uint16_t)(ca2 >> 1);
+                kb_sts16(ea, (kk & 0xffffu) | (uint32_t)(nq + 1));
                 kb_sts32(nsa, (uint32_t)(nq + 1));
             }
         } else {
-            const uint32_t t = (e ^ b.k) & 0xffffu;
+            const uint32_t t = (e ^ kk) & 0xffffu;
             const bool want_last = valid && !is_add && nq > 0;
-            const uint32_t last = *list_at(a.w + 2u * (uint32_t)(want_last ? nq - 1 : 0));
+            const uint32_t last = *list_at(lb + 2u * (uint32_t)(want_last ? nq - 1 : 0));
             const bool add_try = ok && is_add;
             const bool add_go = add_try && e == 0 && nq < C;
             const bool del_go = valid && !is_add && t < 0x2000u;
             const bool move = del_go && (int)t < nq;
             if (add_try && !add_go) bad |= 1u;
-            if (add_go || move) *list_at(a.w + 2u * (uint32_t)(add_go ? nq : (int)t - 1)) = (uint16_t)(add_go ? (ca2 >> 1) : last);
+            if (add_go || move) *list_at(lb + 2u * (uint32_t)(add_go ? nq : (int)t - 1)) = (uint16_t)(add_go ? (ca2 >> 1) : last);
             if (move) kb_sts16(plane + 2u * last, e);
             if (add_go || del_go) {
-                kb_sts16(ea, add_go ? ((b.k & 0xffffu) | (uint32_t)(nq + 1)) : 0u);
+                kb_sts16(ea, add_go ? ((kk & 0xffffu) | (uint32_t)(nq + 1)) : 0u);
                 kb_sts32(nsa, (uint32_t)(add_go ? nq + 1 : nq - 1));
             }
         }
         __syncwarp();
     }
 };
+
+// compact style: the event as a row of the descriptor table.  Row (uint4): byte offset of its first round
+// word, n_rounds | n_writes << 8, writes 0 and 1 (writes 2 and 3 in a second array).  Round word: first op |
+// count << 16 | kind << 24; the next round's operands are requested before the current round runs (the word
+// behind an event's last round is the next event's first or the table's terminator, so the read is harmless).
+template <class M>
+__device__ __forceinline__ void kb_gen_run_compact(KbGenCtx<M>& c, const int pidx, const int k) {
+    const uint4 ev = kb_ldc128(c.tab0 + (uint32_t)M::OFF_EV + 16u * (uint32_t)pidx);
+    c.select_rt(pidx, k);
+    uint32_t rda = c.tab0 + ev.x;
+    uint32_t d = kb_ldc32(rda);
+    uint4 a = c.ldA(d & 0xffffu);
+    KbGenOpB b = c.ldB(d & 0xffffu);
+    const int nw = (int)(ev.y >> 8), nr = (int)(ev.y & 0xffu);
+    if (nw > 0) c.write_rt(0, ev.z);
+    if (nw > 1) c.write_rt(1, ev.w);
+    if (nw > 2) {
+        const uint2 e2 = kb_ldc64(c.tab0 + (uint32_t)M::OFF_EV + 16u * (uint32_t)M::P + 8u * (uint32_t)pidx);
+        c.write_rt(2, e2.x);
+        if (nw > 3) c.write_rt(3, e2.y);
+    }
+    if (nr == 0) __syncwarp();
+    for (int r = 0; r < nr; ++r) {
+        rda += 4u;
+        const uint32_t dn = kb_ldc32(rda);
+        const uint4 an = c.ldA(dn & 0xffffu);
+        const KbGenOpB bn = c.ldB(dn & 0xffffu);
+        M::dispatch(c, d >> 24, (int)((d >> 16) & 0xffu), a, b);
+        d = dn; a = an; b = bn;
+    }
+}
 
 // serial float64 chain over the packed non-zero products: lane adds `tier` entries ending at `top`, the
 // first (tier - own count) of them leading zeros (adding 0.0 is exact, so this is base.mpy:615-618's
@@ -310,11 +379,12 @@ __global__ void __launch_bounds__(M::MAX_THREADS) kb_gen_kernel(const KbGenParam
     c.wb = kb_smem_addr(wb);
     c.lat = kb_smem_addr(wb) + (uint32_t)prm.sm_lat;
     uint8_t* const latp = wb + prm.sm_lat;
+    c.wns = kb_smem_addr(wb) + (uint32_t)prm.sm_ns;
     c.tab0 = kb_smem_addr(kb_sm);
     c.tabA = kb_smem_addr(kb_sm) + 16u * (uint32_t)lane;
-    c.tabK = kb_smem_addr(kb_sm) + 4u * (uint32_t)lane;
+    c.tabB = kb_smem_addr(kb_sm) + (uint32_t)M::OFF_B + (uint32_t)(4 * M::BW) * (uint32_t)lane;
     c.nbT = kb_smem_addr(kb_sm) + (uint32_t)prm.nbt_off;
-    c.lane = lane; c.C = prm.ncells; c.cap = prm.cap;
+    c.lane = lane; c.C = prm.ncells; c.cap = prm.cap; c.capH = (uint32_t)prm.cap >> 1;
     const unsigned lt = kb_lanemask_lt();
 
     for (;;) {  // ---- persistent worker loop: one (epoch, replica) item per iteration ---------------------
@@ -583,38 +653,45 @@ static inline int kb_gen_make_plan(const KbGenInfo& gi, const int size[3], int R
     return 0;
 }
 
-// operand table for one geometry: per round the uint4 array A then the array B (KbGenRoundDesc), then the
-// neighbour table nbT[cell][offset] = 2 * cell index of (cell + offset) under the periodic wrap
+// operand table for one geometry (layout: KbGenInfo), then the neighbour table nbT[cell][offset] = 2 * cell
+// index of (cell + offset) under the periodic wrap
 static inline void kb_gen_fill_tables(const KbGenInfo& gi, const KbGenPlan& pl, uint32_t* out) {
     memset(out, 0, (size_t)pl.tab_bytes);
     unsigned char* base = (unsigned char*)out;
+    uint32_t* rdw = (uint32_t*)(base + gi.off_rd);
     for (int r = 0; r < gi.n_rounds; ++r) {
         const KbGenRoundDesc& rd = gi.rounds[r];
-        const int qw = rd.nc == 0 ? 0 : (1 + 3 * rd.nc + 3) / 4;
+        rdw[r] = (uint32_t)rd.first_op | ((uint32_t)rd.count << 16) | ((uint32_t)rd.kind << 24);
         for (int i = 0; i < rd.count; ++i) {
             const KbGenOpDesc& op = gi.ops[rd.first_op + i];
-            uint32_t* a = (uint32_t*)(base + rd.a_off) + 4 * i;
+            uint32_t* a = (uint32_t*)base + 4 * (rd.first_op + i);
             a[0] = 2u * op.aoff;
             a[1] = (uint32_t)op.cls * (uint32_t)pl.ncells * 2u;
-            a[2] = (uint32_t)pl.sm_ns + 4u * op.q;
-            a[3] = (uint32_t)op.q * (uint32_t)pl.cap * 2u;
-            const uint32_t k = ((uint32_t)op.member << KB_POS_BITS) | (op.is_add ? KB_GEN_KIND_ADD : 0u);
-            if (rd.nc == 0) {
-                ((uint32_t*)(base + rd.b_off))[i] = k;
-            } else {
-                uint32_t* b = (uint32_t*)(base + rd.b_off) + 4 * qw * i;
-                b[0] = k;
-                for (int j = 0; j < rd.nc; ++j) {
-                    if (j < op.ncond) {
-                        b[1 + 3 * j] = 2u * op.coff[j];
-                        b[2 + 3 * j] = (uint32_t)op.cn[j] - 1u;
-                        b[3 + 3 * j] = op.cmask[j];
-                    } else {  // always true: any species of site 1 of the event's own cell
-                        b[1 + 3 * j] = 0; b[2 + 3 * j] = 0; b[3 + 3 * j] = 0xffffffffu;
-                    }
-                }
+            a[2] = 4u * op.q;
+            a[3] = ((uint32_t)op.member << KB_POS_BITS) | (op.is_add ? KB_GEN_KIND_ADD : 0u);
+            uint32_t* b = (uint32_t*)(base + gi.off_b) + gi.bw * (rd.first_op + i);
+            for (int j = 0; j < gi.bw; ++j) {
+                if (j < op.ncond) b[j] = 2u * op.coff[j] | (((uint32_t)op.cn[j] - 1u) << 8) | ((uint32_t)op.cmask[j] << 16);
+                else b[j] = 0xffff0000u;  // always true: any species of site 1 of the event's own cell
             }
         }
+    }
+    rdw[gi.n_rounds] = 0;  // terminator: the prefetch behind the last event's last round reads op 0
+    uint32_t* evw = (uint32_t*)(base + gi.off_ev);
+    uint32_t* ev2 = evw + 4 * gi.n_proc;
+    for (int p = 0; p < gi.n_proc; ++p) {
+        uint32_t w[4];
+        int nw = 0;
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t x = gi.writes[4 * p + i];  // off id | n << 8 | old << 16 | new << 24, 0 = none
+            w[i] = 0;
+            if (!x) continue;
+            w[nw++] = (2u * (x & 255u)) | ((((x >> 8) & 255u) - 1u) << 8) | (x & 0xffff0000u);
+        }
+        evw[4 * p] = (uint32_t)gi.off_rd + 4u * (uint32_t)gi.events[p].first_round;
+        evw[4 * p + 1] = (uint32_t)gi.events[p].n_rounds | ((uint32_t)nw << 8);
+        evw[4 * p + 2] = w[0]; evw[4 * p + 3] = w[1];
+        ev2[2 * p] = w[2]; ev2[2 * p + 1] = w[3];
     }
     uint16_t* nbt = (uint16_t*)(base + pl.nbt_off);
     const int Lx = pl.size[0], Ly = pl.size[1], Lz = pl.size[2];

@@ -82,3 +82,5 @@ if __name__ == "__main__":
         parity()
     if "perf" in what:
         perf()
+    if "ruo2" in what:
+        perf([("ruo2_local_smart", [20, 20], 16384, 5000)])
