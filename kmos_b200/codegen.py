@@ -1,25 +1,28 @@
 """Exporter back end: emit a model's proclist as specialised CUDA (``proclist_<model>.cu``).
 
-kmos writes ``run_proc_nr`` and the ``put_``/``take_`` routines as model-specific straight-line Fortran
+kmos writes ``run_proc_nr`` and the ``put_``/``take_`` routines as model-specific Fortran
 (kmos/io/__init__.py:305-465 write_proclist_run_proc_nr_smart, :2219-2409 write_proclist_put_take,
 :2568-2655 _write_optimal_iftree); ``export_source`` (:3884-3974, hook point :3958-3973) is where the files
 are written.  This module is the CUDA twin of that step for the local_smart backend: from the same rule IR the
 Fortran was parsed into (kmos_b200.fortran_ir -- so statement order, and with it the order of ``avail_sites``,
 is the Fortran's) it emits
 
-  * one ``case`` per process: the site read, the event's ``replace_species`` calls with offsets/species as
-    immediates, then its guarded ``del_proc`` / if-tree ``add_proc`` calls as unrolled *rounds* whose shape
-    (dels only / adds only / mixed, number of dynamic probes, number of ops, operand addresses) is fixed at
-    compile time; event dispatch is a ``switch``;
-  * the static operand descriptions the host turns into the geometry-specialised operand table
-    (``kb_gen_fill_tables`` in csrc/kb_gen.cuh), and the model constants (process count, sites per cell,
-    neighbour offsets) the step skeleton is instantiated with.
+  * the model's compile-time constants (process count, sites per cell, neighbour offsets, probes per add,
+    table layout) and the *lane-group width*: how many lanes step one replica (32, 16 or 8).  The rounds of
+    an event are bounded by the dependency chains of its list operations, not by the number of lanes, so the
+    generator picks the narrowest group that does not lengthen them: the warp then steps 2 or 4 replicas
+    with every instruction;
+  * per process: its ``replace_species`` calls and its guarded ``del_proc`` / if-tree ``add_proc`` calls
+    scheduled into rounds of at most ``lpr`` operations, as static descriptor tables the host turns into the
+    geometry-specialised operand table (``kb_gen_fill_tables`` in csrc/kb_gen.cuh) -- events are rows of a
+    table and not unrolled cases because the replicas of a warp (and the warps of an SM) are in different
+    events at any time: measured, RuO2's 36 unrolled cases (196 KB of SASS) thrash the instruction cache.
 
 The result is compiled with nvcc for sm_100a into ``proclist_<model>_<hash>.so`` (cached by content hash) and
 attached to a batch with ``kmos_b200_batch_attach_proclist``; the table interpreter (kb_smem.cuh) stays the
 path for models this generator declines (``Unsupported``).
 
-    python -m kmos_b200.codegen <model_tables.json | export_dir> [-o out_dir] [--style unrolled|compact] [--build]
+    python -m kmos_b200.codegen <model_tables.json | export_dir> [-o out_dir] [--lpr 8|16|32] [--build]
 """
 import hashlib
 import os
@@ -34,10 +37,12 @@ from .devtables import KIND_ADD, Unsupported
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 CACHE = os.path.join(HERE, "_proclist_cache")
-GEN_VERSION = 3
+GEN_VERSION = 4
 MAX_COND = 4
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
+# threads per CTA the kernel is compiled for (register budget 65536 / threads): narrow groups run fewer warps
+MAX_THREADS = {32: 768, 16: 512, 8: 512}
 
 
 def fnv1a(data):
@@ -51,11 +56,14 @@ def blob_hash(blob):
     return fnv1a(np.ascontiguousarray(blob, dtype="<i4").tobytes())
 
 
-def analyse(ir):
-    """Flatten every process of a local_smart model into writes + rounds of list operations.
+KINDS = {(True, False): "del", (False, True): "add", (True, True): "mixed"}
 
-    -> dict(nproc, offsets, classes, cls_of, member_of, events=[dict(name, anchor_n, writes, rounds)])
-    with rounds = [[op, ...]], op = (kind, q, anchor_off_id, [(off_id, n, mask), ...])."""
+
+def _flatten(ir):
+    """Every process of a local_smart model as writes + list operations in the Fortran's textual order.
+
+    -> dict(nproc, offsets, classes, cls_of, member_of, events=[dict(name, writes, ops)]) with
+    op = (kind, q, anchor_off_id, [(off_id, n, mask), ...], group)."""
     if ir["backend"] != "local_smart":
         raise Unsupported("specialised CUDA is generated for the local_smart backend")
     nproc = len(ir["procs"])
@@ -93,19 +101,15 @@ def analyse(ir):
                               % (p + 1, base_n, proc_anchor[p]))
         if len(writes) > 4:
             raise Unsupported("event writes %d sites" % len(writes))
-        for _k, q, aoff, cs, _g in ops:
+        flat = []
+        for k, q, aoff, cs, grp in ops:
             if aoff[3] != proc_anchor[q - 1]:
                 raise Unsupported("anchor site type mismatch")
             if len(cs) > MAX_COND:
                 raise Unsupported("add with %d dynamic probes" % len(cs))
-        rounds = devtables.schedule_rounds(ops, lambda op: [op[1]],
-                                           lambda op: (cls_of[op[1]], op[2][0], op[2][1], op[2][2]))
-        ev_rounds = []
-        for rnd in rounds:
-            ev_rounds.append([(ops[i][0], ops[i][1], off_id(ops[i][2]),
-                               [(off_id(s), s[3], m) for s, m in ops[i][3]]) for i in rnd])
+            flat.append((k, q, off_id(aoff), [(off_id(s_), s_[3], m) for s_, m in cs], grp, tuple(aoff[:3])))
         events.append({"name": ir["procs"][p], "anchor_n": base_n,
-                       "writes": [(off_id(o), o[3], old, new) for o, old, new in writes], "rounds": ev_rounds})
+                       "writes": [(off_id(o), o[3], old, new) for o, old, new in writes], "ops": flat})
     off_list = [None] * len(offsets)
     for key, i in offsets.items():
         off_list[i] = key
@@ -114,28 +118,57 @@ def analyse(ir):
             "dim": ir["model_dimension"], "species": ir["species"]}
 
 
-KINDS = {(True, False): "del", (False, True): "add", (True, True): "mixed"}
-# estimated SASS instructions of a round body; the event code of the unrolled style must stay inside the SM's
-# instruction cache next to the ~700 instructions of the step skeleton (measured: mini_101 and AB profit from
-# unrolling, RuO2's 12 k instructions thrash the cache -- DESIGN.md 4.1b)
-UNROLL_BUDGET = 1600
+def _schedule(an, lpr):
+    """Rounds of every event for groups of `lpr` lanes -> [[[op, ...], ...], ...] (devtables.schedule_rounds)."""
+    cls_of = an["cls_of"]
+    out = []
+    for ev in an["events"]:
+        ops = ev["ops"]
+        rounds = devtables.schedule_rounds(ops, lambda op: [op[1]], lambda op: (cls_of[op[1]],) + op[5], width=lpr)
+        out.append([[ops[i] for i in rnd] for rnd in rounds])
+    return out
 
 
-def _round_cost(has_del, has_add, nc):
-    return (60 if has_del and has_add else 40 if has_add else 35) + 7 * nc
+def choose_lpr(an):
+    """Lanes per replica: the narrowest group that lengthens the events' rounds (mean over processes) by less
+    than 15 % over a full warp -- the rounds are then set by the dependency chains, and the warp's other lanes
+    step further replicas."""
+    env = os.environ.get("KMOS_B200_GEN_LPR")
+    if env:
+        if int(env) not in (8, 16, 32):
+            raise ValueError("KMOS_B200_GEN_LPR: 8, 16 or 32")
+        return int(env)
+    mean = {}
+    for lpr in (32, 16, 8):
+        rs = _schedule(an, lpr)
+        mean[lpr] = sum(len(r) for r in rs) / float(max(1, len(rs)))
+    for lpr in (8, 16):
+        if mean[lpr] <= 1.15 * mean[32] + 1e-9:
+            return lpr
+    return 32
+
+
+def analyse(ir, lpr=None):
+    """_flatten + the lane-group width + every event's rounds (ev["rounds"] = [[op, ...], ...])."""
+    an = _flatten(ir)
+    an["lpr"] = lpr or choose_lpr(an)
+    for ev, rounds in zip(an["events"], _schedule(an, an["lpr"])):
+        ev["rounds"] = rounds
+    return an
 
 
 def layout(an):
     """Number the ops and rounds in table order and place the table's regions:
-    [A: one uint4 per op][B: bw probe words per op][round words][event rows].  Idle lanes of a round read up
-    to 31 entries past its last op, hence the padding behind A and B."""
+    [A: one word per op][B: bw probe words per op][round words][event rows][write rows].  Idle lanes of a
+    round read up to lpr-1 entries past its last op, hence the padding behind A and B."""
     rounds = []
     first = 0
     ncmax = 0
+    lpr = an["lpr"]
     for e, ev in enumerate(an["events"]):
         for r, rnd in enumerate(ev["rounds"]):
-            if len(rnd) > 32:
-                raise Unsupported("a round with more than 32 ops")
+            if len(rnd) > lpr:
+                raise Unsupported("a round with more than %d ops" % lpr)
             nc = max(len(op[3]) for op in rnd)
             ncmax = max(ncmax, nc)
             rounds.append({"event": e, "round": r, "count": len(rnd), "nc": nc, "first_op": first,
@@ -148,35 +181,25 @@ def layout(an):
     if len(rounds) > 0 and max(len(ev["rounds"]) for ev in an["events"]) > 255:
         raise Unsupported("more than 255 rounds in one event")
     bw = {0: 0, 1: 1, 2: 2, 3: 4, 4: 4}[ncmax]
-    off_b = 16 * (n_ops + 32)
+    off_b = (4 * (n_ops + 32) + 15) // 16 * 16
     off_rd = (off_b + 4 * bw * (n_ops + 32) + 15) // 16 * 16
     off_ev = (off_rd + 4 * (len(rounds) + 1) + 15) // 16 * 16
-    ops_bytes = (off_ev + 24 * an["nproc"] + 15) // 16 * 16
-    # round bodies the model uses, the statically most frequent first
-    variants = {}
-    for rd in rounds:
-        key = (rd["has_del"], rd["has_add"], rd["nc"])
-        variants[key] = variants.get(key, 0) + 1
-    order = sorted(variants, key=lambda k: -variants[k])
-    for rd in rounds:
-        rd["kind"] = order.index((rd["has_del"], rd["has_add"], rd["nc"]))
-    cost = sum(_round_cost(rd["has_del"], rd["has_add"], rd["nc"]) for rd in rounds) + 25 * an["nproc"]
+    off_wr = off_ev + 16 * an["nproc"]
+    ops_bytes = off_wr + 16 * an["nproc"]
     return {"rounds": rounds, "n_ops": n_ops, "bw": bw, "off_b": off_b, "off_rd": off_rd, "off_ev": off_ev,
-            "ops_bytes": ops_bytes, "variants": order, "unrolled_cost": cost}
+            "off_wr": off_wr, "ops_bytes": ops_bytes}
 
 
-def generate(ir, blob=None, name=None, max_threads=768, style="auto"):
-    """-> (CUDA source text, info dict) for a local_smart model IR.  style: "unrolled" (every process its own
-    straight-line case), "compact" (events as descriptor rows over the model's round bodies) or "auto"."""
+def generate(ir, blob=None, name=None, lpr=None):
+    """-> (CUDA source text, info dict) for a local_smart model IR.  lpr: lanes per replica (default: chosen
+    from the model's rounds, or KMOS_B200_GEN_LPR)."""
     if blob is None:
         blob, _info = tables.build_blob(ir)
-    an = analyse(ir)
+    an = analyse(ir, lpr)
     lay = layout(an)
     rounds = lay["rounds"]
-    if style == "auto":
-        style = os.environ.get("KMOS_B200_GEN_STYLE") or ("unrolled" if lay["unrolled_cost"] <= UNROLL_BUDGET else "compact")
-    if style not in ("unrolled", "compact"):
-        raise ValueError("style: unrolled, compact or auto")
+    lpr = an["lpr"]
+    max_threads = MAX_THREADS[lpr]
     fx = ir.get("fixture")
     name = name or ir.get("model_name") or (fx.get("model") if isinstance(fx, dict) else fx) or "model"
     ident = "".join(ch if ch.isalnum() else "_" for ch in name)
@@ -184,99 +207,43 @@ def generate(ir, blob=None, name=None, max_threads=768, style="auto"):
     P = an["nproc"]
     out = []
     w = out.append
-    w("// proclist_%s.cu -- generated by kmos_b200.codegen (version %d, %s style); do not edit." % (
-        ident, GEN_VERSION, style))
-    w("// CUDA twin of the proclist.f90 `kmos export -b local_smart` writes for this model: run_proc_nr as a switch,")
-    w("// every process' replace_species calls and guarded del_proc / if-tree add_proc calls as straight-line code")
-    w("// (kmos/io/__init__.py:305-465, 2219-2409, 2568-2655).  model blob hash %016x" % h)
+    w("// proclist_%s.cu -- generated by kmos_b200.codegen (version %d); do not edit." % (ident, GEN_VERSION))
+    w("// CUDA twin of the proclist.f90 `kmos export -b local_smart` writes for this model: run_proc_nr, every")
+    w("// process' replace_species calls and its guarded del_proc / if-tree add_proc calls (kmos/io/__init__.py:")
+    w("// 305-465, 2219-2409, 2568-2655), scheduled into rounds for groups of %d lanes per replica." % lpr)
+    w("// model blob hash %016x" % h)
     w("#include \"kb_gen.cuh\"")
     w("")
     w("namespace {")
     w("struct KbModel {")
-    w("    static constexpr int P = %d, SPUCK = %d, NOFF = %d, MAX_THREADS = %d;" % (
-        P, an["spuck"], len(an["offsets"]), max_threads))
-    w("    static constexpr int BW = %d, OFF_B = %d, OFF_EV = %d;  // operand table layout" % (
-        lay["bw"], lay["off_b"], lay["off_ev"]))
-    w("    typedef KbGenCtx<KbModel> Ctx;")
+    w("    static constexpr int P = %d, SPUCK = %d, NOFF = %d;" % (P, an["spuck"], len(an["offsets"])))
+    w("    static constexpr int LPR = %d, MAX_THREADS = %d;  // lanes per replica, threads per CTA" % (lpr, max_threads))
+    w("    static constexpr int BW = %d, OFF_B = %d, OFF_EV = %d, OFF_WR = %d;  // operand table layout" % (
+        lay["bw"], lay["off_b"], lay["off_ev"], lay["off_wr"]))
+    w("};")
     by_event = {}
     for rd in rounds:
         by_event.setdefault(rd["event"], []).append(rd)
 
-    def describe(e, ev):
-        w("")
-        w("    // process %d: %s" % (e + 1, ev["name"]))
-        for off, n, old, new in ev["writes"]:
-            w("    //   replace_species(site + (%d,%d,%d) type %d, %s -> %s)" % (
-                an["offsets"][off] + (n, an["species"][old], an["species"][new])))
-
     def ops_text(ops):
         return " ".join(("+" if op[0] == KIND_ADD else "-") + str(op[1]) for op in ops)
 
-    if style == "unrolled":
-        for e, ev in enumerate(an["events"]):
-            describe(e, ev)
-            w("    static __device__ __forceinline__ void ev_%d(Ctx& c, const int k) {" % (e + 1))
-            w("        c.select<%d>(k);" % e)
-            for i, (off, n, old, new) in enumerate(ev["writes"]):
-                w("        c.write<%d, %d, %d, %d, %d>();" % (i, off, n, old, new))
-            rds = by_event.get(e, [])
-
-            def load(j):
-                w("        const uint4 a%d = c.ldA(%d); const KbGenOpB b%d = c.ldB(%d);" % (
-                    j, rds[j]["first_op"], j, rds[j]["first_op"]))
-
-            if rds:
-                load(0)
-            for j, rd in enumerate(rds):
-                if j + 1 < len(rds):
-                    load(j + 1)
-                w("        c.round<%s, %s, %d>(%d, a%d, b%d);  // %s" % (
-                    "true" if rd["has_del"] else "false", "true" if rd["has_add"] else "false", rd["nc"],
-                    rd["count"], j, j, ops_text(ev["rounds"][j])))
-            if not rds:
-                w("        __syncwarp();")
-            w("    }")
+    for e, ev in enumerate(an["events"]):
         w("")
-        w("    static __device__ __forceinline__ void run_event(Ctx& c, const int pidx, const int k) {")
-        w("        switch (pidx) {")
-        for e in range(P):
-            w("        case %d: ev_%d(c, k); break;" % (e, e + 1))
-        w("        default: break;")
-        w("        }")
-        w("    }")
-    else:
-        for e, ev in enumerate(an["events"]):
-            describe(e, ev)
-            for j, rd in enumerate(by_event.get(e, [])):
-                w("    //   round %d (%s, %d probes): %s" % (
-                    j, KINDS[(rd["has_del"], rd["has_add"])], rd["nc"], ops_text(ev["rounds"][j])))
-        w("")
-        w("    // the round bodies this model uses; kind = position in this switch")
-        w("    static __device__ __forceinline__ void dispatch(Ctx& c, const uint32_t kind, const int count,")
-        w("                                                    const uint4 a, const KbGenOpB& b) {")
-        if len(lay["variants"]) <= 1:
-            for hd, ha, nc in lay["variants"]:
-                w("        c.round<%s, %s, %d>(count, a, b);" % ("true" if hd else "false", "true" if ha else "false", nc))
-            if not lay["variants"]:
-                w("        __syncwarp();")
-        else:
-            w("        switch (kind) {")
-            for i, (hd, ha, nc) in enumerate(lay["variants"]):
-                w("        %s c.round<%s, %s, %d>(count, a, b); break;  // %s" % (
-                    "default:" if i == len(lay["variants"]) - 1 else "case %d:" % i,
-                    "true" if hd else "false", "true" if ha else "false", nc, KINDS[(hd, ha)]))
-            w("        }")
-        w("    }")
-        w("    static __device__ __forceinline__ void run_event(Ctx& c, const int pidx, const int k) {")
-        w("        kb_gen_run_compact<KbModel>(c, pidx, k);")
-        w("    }")
-    w("};")
+        w("// process %d: %s" % (e + 1, ev["name"]))
+        for off, n, old, new in ev["writes"]:
+            w("//   replace_species(site + (%d,%d,%d) type %d, %s -> %s)" % (
+                an["offsets"][off] + (n, an["species"][old], an["species"][new])))
+        for j, rd in enumerate(by_event.get(e, [])):
+            w("//   round %d (%s, %d probes): %s" % (
+                j, KINDS[(rd["has_del"], rd["has_add"])], rd["nc"], ops_text(ev["rounds"][j])))
     w("")
     w("const KbGenOpDesc kb_ops[] = {")
     n_ops = 0
     for e, ev in enumerate(an["events"]):
         for rnd in ev["rounds"]:
-            for kind, q, aoff, cs in rnd:
+            for op in rnd:
+                kind, q, aoff, cs = op[0], op[1], op[2], op[3]
                 co = [c[0] for c in cs] + [0] * (MAX_COND - len(cs))
                 cn = [c[1] for c in cs] + [0] * (MAX_COND - len(cs))
                 cm = [c[2] for c in cs] + [0] * (MAX_COND - len(cs))
@@ -290,7 +257,7 @@ def generate(ir, blob=None, name=None, max_threads=768, style="auto"):
     w("};")
     w("const KbGenRoundDesc kb_rounds[] = {")
     for rd in rounds:
-        w("    {%d, %d, %d, %d}," % (rd["first_op"], rd["count"], rd["nc"], rd["kind"]))
+        w("    {%d, %d, %d, 0}," % (rd["first_op"], rd["count"], rd["nc"]))
     if not rounds:
         w("    {0, 0, 0, 0},")
     w("};")
@@ -311,24 +278,23 @@ def generate(ir, blob=None, name=None, max_threads=768, style="auto"):
     w("const uint8_t kb_proc_member[] = {%s};" % ", ".join(str(an["member_of"][q]) for q in range(1, P + 1)))
     w("const KbGenInfo kb_info = {KB_GEN_ABI, %d, %d, %d, %d, %d, %d, %d, %d," % (
         P, an["n_species"], an["spuck"], an["dim"], len(an["offsets"]), len(an["classes"]), n_ops, len(rounds)))
-    w("                           %d, %d, %d, %d, %d, %d, %d, 0x%016xull, \"%s\"," % (
-        lay["bw"], lay["off_b"], lay["off_rd"], lay["off_ev"], lay["ops_bytes"], max_threads,
-        1 if style == "compact" else 0, h, ident))
+    w("                           %d, %d, %d, %d, %d, %d, %d, %d, 0x%016xull, \"%s\"," % (
+        lay["bw"], lay["off_b"], lay["off_rd"], lay["off_ev"], lay["off_wr"], lay["ops_bytes"], max_threads,
+        lpr, h, ident))
     w("                           kb_ops, kb_rounds, kb_events, kb_offsets, kb_writes, kb_proc_cls, kb_proc_member};")
     w("}  // namespace")
     w("")
     w("KB_GEN_MODULE(KbModel, kb_info)")
     w("")
     info = {"name": ident, "hash": h, "n_ops": n_ops, "n_rounds": len(rounds), "ops_bytes": lay["ops_bytes"],
-            "n_classes": len(an["classes"]), "n_offsets": len(an["offsets"]), "style": style,
-            "unrolled_cost": lay["unrolled_cost"], "variants": lay["variants"],
+            "n_classes": len(an["classes"]), "n_offsets": len(an["offsets"]), "lpr": lpr,
             "rounds_per_event": [len(ev["rounds"]) for ev in an["events"]]}
     return "\n".join(out), info
 
 
-def write_source(ir, out_dir, blob=None, name=None, max_threads=768, style="auto"):
+def write_source(ir, out_dir, blob=None, name=None, lpr=None):
     """Write proclist_<model>.cu into `out_dir` (next to the exported Fortran); returns its path."""
-    src, info = generate(ir, blob, name, max_threads, style)
+    src, info = generate(ir, blob, name, lpr)
     path = os.path.join(out_dir, "proclist_%s.cu" % info["name"])
     with open(path, "w") as f:
         f.write(src)
@@ -343,58 +309,64 @@ def _skeleton_digest():
     return hsh
 
 
-def build(ir, blob=None, name=None, out_dir=None, max_threads=768, verbose=False, style="auto"):
+def _so_path(src, info, out_dir):
+    hsh = _skeleton_digest()
+    hsh.update(src.encode())
+    hsh.update(" ".join(NVCC_FLAGS).encode())
+    return os.path.join(out_dir or CACHE, "proclist_%s_%s.so" % (info["name"], hsh.hexdigest()[:16]))
+
+
+def build(ir, blob=None, name=None, out_dir=None, verbose=False, lpr=None):
     """Generate and compile; the shared object is cached under the content hash of source + skeleton.
 
     -> path of proclist_<model>_<hash>.so"""
-    src, info = generate(ir, blob, name, max_threads, style)
-    hsh = _skeleton_digest()
-    hsh.update(src.encode())
-    hsh.update(" ".join(NVCC_FLAGS).encode())
-    tag = hsh.hexdigest()[:16]
-    out_dir = out_dir or CACHE
-    os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, "proclist_%s_%s.so" % (info["name"], tag))
+    src, info = generate(ir, blob, name, lpr)
+    so = _so_path(src, info, out_dir)
+    os.makedirs(os.path.dirname(so), exist_ok=True)
     if os.path.exists(so):
         return so
-    cu = os.path.join(out_dir, "proclist_%s_%s.cu" % (info["name"], tag))
+    cu = so[:-3] + ".cu"
     with open(cu, "w") as f:
         f.write(src)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", CSRC, "-o", so + ".tmp", cu]
+    tmp = "%s.%d.tmp" % (so, os.getpid())
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", CSRC, "-o", tmp, cu]
     subprocess.check_call(cmd)
-    os.replace(so + ".tmp", so)
+    os.replace(tmp, so)
     return so
 
 
-def find_built(ir, blob=None, name=None, out_dir=None, max_threads=768, style="auto"):
+def find_built(ir, blob=None, name=None, out_dir=None, lpr=None):
     """Path of the cached shared object for this model, or None (no compiler is invoked)."""
-    src, info = generate(ir, blob, name, max_threads, style)
-    hsh = _skeleton_digest()
-    hsh.update(src.encode())
-    hsh.update(" ".join(NVCC_FLAGS).encode())
-    so = os.path.join(out_dir or CACHE, "proclist_%s_%s.so" % (info["name"], hsh.hexdigest()[:16]))
+    src, info = generate(ir, blob, name, lpr)
+    so = _so_path(src, info, out_dir)
     return so if os.path.exists(so) else None
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if not a.startswith("-")]
-    do_build = "--build" in sys.argv
-    style = "auto"
-    if "--style" in sys.argv:
-        style = sys.argv[sys.argv.index("--style") + 1]
-        args = [a for a in args if a != style]
+    argv = sys.argv[1:]
+    do_build = "--build" in argv
+    lpr_arg = None
     out = None
-    if "-o" in sys.argv:
-        out = sys.argv[sys.argv.index("-o") + 1]
-        args = [a for a in args if a != out]
+    args = []
+    i = 0
+    while i < len(argv):
+        if argv[i] == "--lpr":
+            lpr_arg = int(argv[i + 1]); i += 2
+        elif argv[i] == "-o":
+            out = argv[i + 1]; i += 2
+        elif argv[i].startswith("-"):
+            i += 1
+        else:
+            args.append(argv[i]); i += 1
     src_path = args[0]
     if os.path.isdir(src_path):
         src_path = os.path.join(src_path, "model_tables.json")
     model_ir = tables.load_ir(src_path)
     out = out or os.path.dirname(os.path.abspath(src_path))
-    path, inf = write_source(model_ir, out, style=style)
-    print("%s: %s style, %d ops in %d rounds, %d table bytes" % (path, inf["style"], inf["n_ops"], inf["n_rounds"],
-                                                             inf["ops_bytes"]))
+    os.makedirs(out, exist_ok=True)
+    path, inf = write_source(model_ir, out, lpr=lpr_arg)
+    print("%s: %d lanes per replica, %d ops in %d rounds, %d table bytes" % (
+        path, inf["lpr"], inf["n_ops"], inf["n_rounds"], inf["ops_bytes"]))
     if do_build:
-        print(build(model_ir, verbose=True, style=style))
+        print(build(model_ir, verbose=True, lpr=lpr_arg))

@@ -55,7 +55,7 @@ struct KbGenModule {
     const KbGenInfo* info = nullptr;
     int (*plan)(const int32_t*, int32_t, int32_t, KbGenPlan*) = nullptr;
     int (*build_tables)(const KbGenPlan*, uint32_t*) = nullptr;
-    int (*launch)(const KbGenParams*, int, int, int, void*) = nullptr;
+    int (*launch)(const KbGenParams*, const KbGenPlan*, int*, int, int, void*) = nullptr;
 };
 
 struct kmos_b200_batch {
@@ -561,7 +561,7 @@ static int auto_kernel(const kmos_b200_batch* b) {
         // instructions per step; the HBM warp kernel wins only when few replicas fit into shared memory
         double hbm_warps = (double)b->R / (double)(b->sm_count > 0 ? b->sm_count : 1);
         if (hbm_warps > 24.0) hbm_warps = 24.0;
-        const double gen_score = (double)b->gp.wpc * b->gp.ctas_per_sm;
+        const double gen_score = (double)b->gp.replicas_per_cta * b->gp.ctas_per_sm;
         if (!b->li_ok || 0.4 * hbm_warps <= gen_score) return KMOS_B200_KERNEL_GENERATED;
     }
     if (b->smem_ok && b->li_ok) {
@@ -693,9 +693,9 @@ extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[12]) {
         if (info[7] > (int64_t)b->sm_count * b->ctas_per_sm) info[7] = (int64_t)b->sm_count * b->ctas_per_sm;
         info[8] = b->sp.p1_global; info[9] = b->regs; info[10] = b->sp.split; info[11] = b->sp.img_bytes;
     } else if (b->kernel == KMOS_B200_KERNEL_GENERATED) {
-        info[1] = b->gp.wpc; info[2] = b->gp.smem_bytes; info[3] = b->gp.ctas_per_sm; info[4] = b->gp.sm_count;
+        info[1] = b->gp.replicas_per_cta; info[2] = b->gp.smem_bytes; info[3] = b->gp.ctas_per_sm; info[4] = b->gp.sm_count;
         info[5] = b->gp.rep_bytes; info[6] = b->gp.tab_bytes;
-        info[7] = (b->R + b->gp.wpc - 1) / b->gp.wpc;
+        info[7] = (b->R + b->gp.replicas_per_cta - 1) / b->gp.replicas_per_cta;
         if (info[7] > (int64_t)b->gp.sm_count * b->gp.ctas_per_sm) info[7] = (int64_t)b->gp.sm_count * b->gp.ctas_per_sm;
         info[8] = 1; info[9] = b->gp.regs; info[10] = 0; info[11] = b->gp.img_bytes;
     } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM && b->otf_ok) {
@@ -935,7 +935,7 @@ extern "C" int kmos_b200_batch_attach_proclist(kmos_b200_batch* b, const char* s
     auto info_fn = (const KbGenInfo* (*)(void))dlsym(g.handle, "kmos_b200_gen_info");
     g.plan = (int (*)(const int32_t*, int32_t, int32_t, KbGenPlan*))dlsym(g.handle, "kmos_b200_gen_plan");
     g.build_tables = (int (*)(const KbGenPlan*, uint32_t*))dlsym(g.handle, "kmos_b200_gen_build_tables");
-    g.launch = (int (*)(const KbGenParams*, int, int, int, void*))dlsym(g.handle, "kmos_b200_gen_launch");
+    g.launch = (int (*)(const KbGenParams*, const KbGenPlan*, int*, int, int, void*))dlsym(g.handle, "kmos_b200_gen_launch");
     auto fail = [&](int code, const std::string& msg) { dlclose(g.handle); return set_err(code, "attach_proclist: " + msg); };
     if (!info_fn || !g.plan || !g.build_tables || !g.launch) return fail(KMOS_B200_ERR_ARG, "not a kmos_b200 proclist module");
     g.info = info_fn();
@@ -987,42 +987,21 @@ static int launch_generated(kmos_b200_batch* b, long long n) {
     const KbGenPlan& gp = b->gp;
     KbGenParams p;
     memset(&p, 0, sizeof p);
-    p.tab = b->d_gen_tab; p.tab_bytes = gp.tab_bytes; p.nbt_off = gp.nbt_off;
+    p.tab = b->d_gen_tab; p.tab_bytes = gp.tab_bytes; p.nbt_off = gp.nbt_off; p.mbar_off = gp.mbar_off;
     p.ncells = gp.ncells; p.cap = gp.cap;
     p.lattice = b->lattice; p.nsites = b->nsites; p.image = b->gen_image; p.rates = b->rates; p.integ = b->integ;
     p.procstat = b->procstat; p.sc = b->sc; p.writes = b->d_gen_writes; p.R = b->R; p.nsteps = n;
-    p.rep_bytes = gp.rep_bytes; p.sm_lat = gp.sm_lat; p.sm_ns = gp.sm_ns; p.sm_prod = gp.sm_prod; p.sm_rng = gp.sm_rng;
-    p.sm_mbar = gp.sm_mbar; p.stage_off = gp.stage_off; p.stage_bytes = gp.stage_bytes; p.lat_stride = gp.lat_stride;
+    p.rep_bytes = gp.rep_bytes; p.warp_bytes = gp.warp_bytes; p.sm_lat = gp.sm_lat; p.sm_ns = gp.sm_ns;
+    p.sm_win = gp.sm_win; p.sm_prod = gp.sm_prod;
+    p.stage_off = gp.stage_off; p.stage_bytes = gp.stage_bytes; p.lat_stride = gp.lat_stride;
     p.img_bytes = gp.img_bytes;
     const char* nb = getenv("KMOS_B200_NO_BULK");
     p.use_bulk = (nb && nb[0] == '1') ? 0 : 1;
-    int wpc = gp.wpc;
+    // launch geometry (persistent CTAs, epochs) is the module's: it knows how many replicas a warp steps
     const char* wenv = getenv("KMOS_B200_WARPS_PER_CTA");
-    if (wenv && atoi(wenv) > 0 && atoi(wenv) <= gp.wpc) wpc = atoi(wenv);
-    const int smem = gp.tab_bytes + wpc * gp.rep_bytes;
-    int blocks = (b->R + wpc - 1) / wpc;
-    const int resident = gp.sm_count * gp.ctas_per_sm;
-    if (blocks > resident) blocks = resident;
-    const long long slots = (long long)blocks * wpc;
-    long long epochs = 1;
-    if (b->R > slots) {
-        epochs = (24 * slots + b->R - 1) / b->R;
-        const long long max_epochs = n / 256 > 0 ? n / 256 : 1;
-        if (epochs > max_epochs) epochs = max_epochs;
-        if (epochs > 64) epochs = 64;
-        if (epochs < 1) epochs = 1;
-    }
     const char* ep_env = getenv("KMOS_B200_EPOCHS");
-    if (ep_env && atoi(ep_env) > 0) epochs = atoi(ep_env);
-    if ((n + epochs - 1) / epochs > 0x40000000LL) epochs = (n + 0x3fffffffLL) / 0x40000000LL;
-    p.chunk = (n + epochs - 1) / epochs;
-    epochs = (n + p.chunk - 1) / p.chunk;
-    if (epochs * (long long)b->R > 0x7fffffffLL) return set_err(KMOS_B200_ERR_ARG, "do_kmc_steps: too many work items");
-    p.n_items = (int)(epochs * b->R);
-    p.work_counter = b->d_sched;
-    p.done = b->d_sched + 1;
-    CU(cudaMemsetAsync(b->d_sched, 0, ((size_t)b->R + 1) * sizeof(int), b->stream));
-    const int lrc = b->gen.launch(&p, blocks, wpc * 32, smem, (void*)b->stream);
+    const int lrc = b->gen.launch(&p, &gp, b->d_sched, wenv ? atoi(wenv) : 0, ep_env ? atoi(ep_env) : 0, (void*)b->stream);
+    if (lrc == -1) return set_err(KMOS_B200_ERR_ARG, "do_kmc_steps: too many work items");
     if (lrc != 0) return set_err(KMOS_B200_ERR_CUDA, std::string("generated kernel launch: ") + cudaGetErrorString((cudaError_t)lrc));
     return KMOS_B200_OK;
 }

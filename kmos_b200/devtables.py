@@ -175,21 +175,43 @@ def exclusive(ca, cb):
 
 
 def exclusivity_classes(ir, proc_anchor):
-    """Greedy clique cover of the `mutually exclusive` relation -> (classes, cls_of, member_of)."""
+    """Smallest clique cover of the `mutually exclusive` relation -> (classes, cls_of, member_of).
+
+    Every class costs one uint16 plane of ncells entries in shared memory, so the cover is searched exactly
+    (depth first, first-fit order, bounded number of nodes; the first leaf is the greedy first-fit cover, so a
+    cut-off search is never worse than that).  RuO2: 6 classes instead of first-fit's 7."""
     nproc = len(ir["procs"])
     conds = process_conditions(ir)
-    classes = []
-    for q in range(1, nproc + 1):
-        placed = False
-        if q in conds:
-            for cl in classes:
-                if len(cl) < MAX_CLASS_MEMBERS and proc_anchor[cl[0] - 1] == proc_anchor[q - 1] and \
-                        all(c in conds and exclusive(conds[q], conds[c]) for c in cl):
-                    cl.append(q)
-                    placed = True
-                    break
-        if not placed:
-            classes.append([q])
+
+    def excl(a, b):
+        return a in conds and b in conds and proc_anchor[a - 1] == proc_anchor[b - 1] and \
+            exclusive(conds[a], conds[b])
+
+    nodes = list(range(1, nproc + 1))
+    best = [None]
+    budget = [200000]
+
+    def rec(i, classes):
+        if best[0] is not None and len(classes) >= len(best[0]):
+            return
+        if i == len(nodes):
+            best[0] = [list(c) for c in classes]
+            return
+        budget[0] -= 1
+        if budget[0] < 0 and best[0] is not None:
+            return
+        q = nodes[i]
+        for cl in classes:
+            if len(cl) < MAX_CLASS_MEMBERS and all(excl(q, c) for c in cl):
+                cl.append(q)
+                rec(i + 1, classes)
+                cl.pop()
+        classes.append([q])
+        rec(i + 1, classes)
+        classes.pop()
+
+    rec(0, [])
+    classes = best[0]
     cls_of, member_of = {}, {}
     for ci, cl in enumerate(classes):
         for mi, q in enumerate(cl):
@@ -198,7 +220,7 @@ def exclusivity_classes(ir, proc_anchor):
     return classes, cls_of, member_of
 
 
-def schedule_rounds(ops, lists_of, entry_of):
+def schedule_rounds(ops, lists_of, entry_of, width=None):
     """List scheduling into rounds of at most WARP ops (one op per lane, rounds separated by __syncwarp).
 
     Ordering that must be kept from the reference's textual order:
@@ -230,7 +252,7 @@ def schedule_rounds(ops, lists_of, entry_of):
         while True:
             if r == len(rounds):
                 rounds.append([])
-            if len(rounds[r]) < WARP:
+            if len(rounds[r]) < (width or WARP):
                 break
             r += 1
         rounds[r].append(i)
