@@ -154,6 +154,115 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------------
+# the five BASELINE.json configurations (configs[2] = C is the headline; the others are reported in "configs")
+# --------------------------------------------------------------------------------------------------
+CONFIGS = [
+    # key, label, fixture, lattice, replicas, kMC steps per timed launch
+    ("A", "mini_101 fcc_100 CO adsorption/desorption, local_smart", "mini_101_local_smart", [20, 20], 16384, 20000),
+    ("B", "ZGB 64x64, local_smart, y_CO sweep", "zgb_local_smart", [64, 64], 4096, 4000),
+    ("C", "RuO2(110) CO oxidation 20x20, local_smart (headline)", MODEL, SIZE, REPLICAS_PER_GPU, 5000),
+    ("D", "pairwise interaction 128x128, lat_int", "pairwise_lat_int", [128, 128], 2048, 4000),
+    ("E", "pairwise interaction 256x256, otf", "pairwise_otf_otf", [256, 256], 3552, 40),
+]
+# dram bytes per launch of the dominant kernel, from the committed `ncu --set full` summaries
+NCU_SUMMARIES = {"C": "ncu_summary_r2.json", "D": "ncu_latint_kernel_r1.json", "E": "ncu_otf_kernel_r1.json"}
+
+
+def _counter_worker(args):
+    name, size, n = args
+    from kmos_b200 import tables, workloads
+    from oracle import oracle
+    ir = tables.load_ir(os.path.join(REPO, "tests", "golden", "models", name + ".json"))
+    blob, _info = tables.build_blob(ir)
+    r = workloads.rates_for(name.split("_")[0], ir, 64)[32]
+    o = oracle.Oracle(blob, size, seed=99, replica=0, rates=r)
+    o.do_steps(n // 4)
+    o.reset_counters()
+    o.do_steps(n)
+    c = o.counters
+    return {k: c[k] / float(n) for k in ("n_rs", "n_chk", "n_del", "n_gs", "n_add")}, len(ir["procs"])
+
+
+def config_counters():
+    """Per-step event counters of configs A, B and D from a short oracle run each, in forked
+    workers before CUDA is initialised.  -> {key: (counters, P)}"""
+    import multiprocessing as mp
+    jobs = [(k, (name, size, 20000)) for k, _l, name, size, _R, _n in CONFIGS if k in "ABD"]
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        res = pool.map(_counter_worker, [j[1] for j in jobs])
+    return {k: r for (k, _), r in zip(jobs, res)}
+
+
+def _ncu_dram_bytes(key):
+    try:
+        with open(os.path.join(REPO, "profiles", NCU_SUMMARIES[key])) as f:
+            d = json.load(f)
+    except (KeyError, OSError, ValueError):
+        return None, None
+    if "dram_bytes_per_launch" in d:
+        return d["dram_bytes_per_launch"], d.get("launch")
+    conv = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    try:
+        tot = sum(float(d[k]["value"].replace(",", "")) * conv[d[k]["unit"]]
+                  for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        return tot, "profiles/" + NCU_SUMMARIES[key]
+    except (KeyError, ValueError):
+        return None, None
+
+
+def measure_configs(counters, headline_entry, device, smem_peak, hbm_peak):
+    """Throughput of the other four BASELINE configurations, device-resident state, CUDA events, about a
+    second each, after the headline's timed region.  -> list of 5 entries (C = the headline's own numbers)."""
+    from kmos_b200 import engine, otf as otf_mod, tables, workloads
+    out = []
+    for key, label, name, size, R, n in CONFIGS:
+        if key == "C":
+            out.append(headline_entry)
+            continue
+        ir = tables.load_ir(os.path.join(REPO, "tests", "golden", "models", name + ".json"))
+        m = engine.Model(ir=ir)
+        rates = workloads.rates_for(name.split("_")[0], ir, R)
+        lut = None
+        if ir["backend"] == "otf":
+            lut = np.tile(otf_mod.build_lut(ir, m.info, rates[0]), (R, 1))
+        b = engine.Batch(m, R, size, device=device, rates=rates, lut=lut)
+        b.do_steps(max(n // 4, 1))
+        b.synchronize()
+        ns0 = b.nr_of_sites.sum(axis=1).mean() if key == "E" else 0.0
+        times = []
+        for _ in range(2):
+            b.timer_start()
+            b.do_steps(n)
+            times.append(b.timer_stop())
+        ms = float(np.mean(times))
+        info = b.kernel_info()
+        ok = bool((b.status == 0).all())
+        if key == "E":
+            # otf: every live entry of rates_matrix is re-added every step (base_otf.f90:687-717)
+            ns1 = b.nr_of_sites.sum(axis=1).mean()
+            b_step = 8.0 * 0.5 * (ns0 + ns1)
+        else:
+            cnt, P = counters[key]
+            b_step = algorithmic_bytes_per_step(P, cnt)
+        b.close()
+        m.close()
+        launch_bytes = b_step * R * n
+        achieved = launch_bytes / (ms * 1e-3) / 1e9
+        in_smem = info["kernel_name"] in ("generated", "smem")
+        peak = smem_peak if in_smem else hbm_peak
+        traffic, traffic_src = _ncu_dram_bytes(key)
+        out.append({
+            "config": key, "workload": label, "model": name, "lattice": size, "replicas": R,
+            "kmc_steps_per_launch": n, "kernel": info["kernel_name"], "replicas_per_cta": info["replicas_per_cta"],
+            "value": R * n / (ms * 1e-3), "unit": UNIT, "ms_per_launch": ms, "all_replicas_ok": ok,
+            "roofline": {"bound": "smem" if in_smem else "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_kmc_step": b_step}})
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -175,8 +284,9 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": float(np.mean([w for _, w in vals]) * 1e3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
-        "config": workload_config(grid, args, extra={"note": "reference semantics on host cores (CPU port of "
-                                                    "the generated Fortran; no Fortran compiler in this image)"}),
+        "config": workload_config(grid, args),
+        "note": "reference semantics on host cores (CPU port of the generated Fortran, gcc -O3; neither this "
+                "image nor the GPU box has a Fortran compiler: profiles/fortran_probe_r2.txt)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -184,26 +294,29 @@ def run_reference(args, rank, world):
     _emit(line)
 
 
-def workload_config(grid, args, extra=None):
-    cfg = {"workload": "RuO2(110) CO oxidation 20x20 (examples/render_co_oxidation_ruo2.py), local_smart, "
-                       "%d replicas/GPU = %d T x %d p_CO x %d seeds" % (REPLICAS_PER_GPU, N_T, N_P, SEEDS),
-           "replicas_per_gpu": REPLICAS_PER_GPU, "lattice": SIZE, "processes": 36,
-           "kmc_steps_per_replica_per_step": args.inner,
-           "T_K": [grid["T"][0], grid["T"][-1]], "p_CO_bar": [grid["p_COgas"][0], grid["p_COgas"][-1]],
-           "p_O2_bar": grid["p_O2gas"], "rng": "Philox4x32-10 per replica",
-           "parallelism": "replica-sharded, %d GPU(s), NCCL tally all-reduce per step" % args.gpus}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def workload_config(grid, args):
+    """The same dictionary in both arms: what is computed, not how."""
+    return {"workload": "RuO2(110) CO oxidation 20x20 (examples/render_co_oxidation_ruo2.py), local_smart, "
+                        "%d replicas/GPU = %d T x %d p_CO x %d seeds" % (REPLICAS_PER_GPU, N_T, N_P, SEEDS),
+            "replicas_per_gpu": REPLICAS_PER_GPU, "lattice": SIZE, "processes": 36,
+            "kmc_steps_per_replica_per_step": args.inner,
+            "T_K": [grid["T"][0], grid["T"][-1]], "p_CO_bar": [grid["p_COgas"][0], grid["p_COgas"][-1]],
+            "p_O2_bar": grid["p_O2gas"], "rng": "Philox4x32-10 per replica",
+            "parallelism": "replica-sharded, %d GPU(s), tally all-reduce per step (int64 counts + f64 sums)" % args.gpus,
+            # timing rule: inputs larger than L2 -- every bench step streams each replica's whole state
+            # (avail_sites incl. the L2-resident lists, lattice, per-process arrays: > 28 KB per replica)
+            "l2": "no flush: the state a step touches (> %d MB/GPU) exceeds the 126 MB L2"
+                  % (REPLICAS_PER_GPU * 28 * 1024 // 2**20)}
 
 
 def run_ours(args, rank, world, local_rank):
     ir, blob, info, rates, group_of, grid = load_workload()
     P = len(ir["procs"])
 
-    # ---- CPU baseline first (before CUDA is initialised in this process: the pool forks) ----------------
+    # ---- CPU legs first (before CUDA is initialised in this process: the pools fork) --------------------
     cpu = None
     counters = None
+    cfg_counters = None
     if rank == 0:
         cores = host_cores()
         n_rep, warm, n = 4 * cores, 20000, args.cpu_steps
@@ -212,9 +325,11 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d replicas spread over the grid x %d steps (after %d warm-up), %.1f s wall"
                              % (n_rep, n, warm, wall)}
+            if not args.no_configs:
+                cfg_counters = config_counters()
 
     import torch
-    from kmos_b200 import engine
+    from kmos_b200 import engine, parallel
 
     if world > 1:
         import torch.distributed as dist
@@ -222,15 +337,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     stream = torch.cuda.Stream()
     model = engine.Model(ir=ir, blob=blob, info=info)
-    seeds = (np.arange(REPLICAS_PER_GPU, dtype=np.uint64) + np.uint64(rank * REPLICAS_PER_GPU)) * np.uint64(2654435761) + np.uint64(17)
-    ids = (np.arange(REPLICAS_PER_GPU) + rank * REPLICAS_PER_GPU).astype(np.uint32)
-    batch = engine.Batch(model, REPLICAS_PER_GPU, SIZE, device=local_rank, seeds=seeds, replica_ids=ids, rates=rates)
-    batch.set_stream(stream.cuda_stream)
-    kinfo = batch.kernel_info()
-    assert kinfo["kernel_name"] == "smem", kinfo
     n_groups = N_T * N_P
-    words = batch.tally_words()
-    tally = torch.zeros(n_groups * words, dtype=torch.float64, device="cuda")
+    nocc = model.n_species * model.spuck
+    count_cols = parallel.count_columns(P, nocc)
     smem_peak, _mhz = engine.measure_smem_bandwidth(local_rank)
 
     def barrier():
@@ -238,57 +347,85 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(kernel_events=None):
-        with torch.cuda.stream(stream):
-            if kernel_events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-            batch.do_steps(args.inner)
-            if kernel_events is not None:
-                e1.record(stream)
-                kernel_events.append((e0, e1))
-            batch.reduce_tallies(group_of, n_groups, dev_ptr=tally.data_ptr(), want_host=False)
-            if world > 1:
-                dist.all_reduce(tally)
+    def make_batch(first, count):
+        """Replicas [first, first+count) of the global id space, their rows of the rate matrix."""
+        gid = np.arange(first, first + count)
+        seeds = gid.astype(np.uint64) * np.uint64(2654435761) + np.uint64(17)
+        rows = np.ascontiguousarray(rates[gid % REPLICAS_PER_GPU])
+        b = engine.Batch(model, count, SIZE, device=local_rank, seeds=seeds, replica_ids=gid.astype(np.uint32), rates=rows)
+        b.set_stream(stream.cuda_stream)
+        return b, np.ascontiguousarray(group_of[gid % REPLICAS_PER_GPU]), rows
 
-    # ---- device-resident throughput ("value") -----------------------------------------------------------
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
+    def timed_region(batch, groups, tally, steps, warmup, kernel_events=None):
+        def one_step(kev=None):
+            with torch.cuda.stream(stream):
+                if kev is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                batch.do_steps(args.inner)
+                if kev is not None:
+                    e1.record(stream)
+                    kev.append((e0, e1))
+                batch.reduce_tallies(groups, n_groups, dev_ptr=tally.data_ptr(), want_host=False)
+                parallel.all_reduce_tallies(tally, count_cols=count_cols)
+        for _ in range(warmup):
+            one_step()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record(stream)
+        for _ in range(steps):
+            one_step(kernel_events)
+        t1.record(stream)
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- weak scaling: every rank owns REPLICAS_PER_GPU replicas; device-resident throughput ("value") ---
+    batch, groups, rate_rows = make_batch(rank * REPLICAS_PER_GPU, REPLICAS_PER_GPU)
+    kinfo = batch.kernel_info()
+    assert kinfo["kernel_name"] == "generated", kinfo
+    words = batch.tally_words()
+    tally = torch.zeros((n_groups, words), dtype=torch.float64, device="cuda")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     kev = []
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record(stream)
-    for _ in range(args.steps):
-        one_step(kev)
-    t1.record(stream)
-    barrier()
-    ms = t0.elapsed_time(t1)
+    ms = timed_region(batch, groups, tally, args.steps, args.warmup, kev)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([kernel_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, kernel_ms = t.tolist()
+        kernel_ms = float(t.item())
     status_ok = bool(np.all(batch.status == 0))
     steps_done = int(batch.kmc_step.min())
+    # the all-reduced tally of the last step must account for every replica and step of every rank
+    tl = batch.split_tally(tally.cpu().numpy())
+    checks = {"all_replicas_ok": status_ok, "kmc_steps_per_replica_total": steps_done,
+              "tally_n_replicas": float(tl["n_replicas"].sum()), "tally_kmc_steps": float(tl["kmc_steps"].sum()),
+              "tally_events": float(tl["procstat"].sum())}
+    assert checks["tally_n_replicas"] == world * REPLICAS_PER_GPU, checks
+    if status_ok:
+        assert checks["tally_kmc_steps"] == checks["tally_events"] == float(world) * REPLICAS_PER_GPU * steps_done, checks
 
     # ---- end to end through the public API with host buffers ("e2e") -------------------------------------
-    pinned = torch.from_numpy(np.ascontiguousarray(rates)).pin_memory()
+    pinned = torch.from_numpy(np.ascontiguousarray(rate_rows)).pin_memory()
     rates_pinned = pinned.numpy()
     host_tally = np.zeros((n_groups, words))
 
     def one_step_e2e():
         batch.set_rates(rates_pinned)                       # H2D of this step's inputs (pinned host memory)
         batch.do_steps(args.inner)
-        t = batch.reduce_tallies(group_of, n_groups, dev_ptr=tally.data_ptr(), want_host=(world == 1))
+        t = batch.reduce_tallies(groups, n_groups, dev_ptr=tally.data_ptr(), want_host=(world == 1))
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.all_reduce(tally)
-                t = tally.cpu().numpy().reshape(n_groups, words)  # D2H of the step's result
+                parallel.all_reduce_tallies(tally, count_cols=count_cols)
+                t = tally.cpu().numpy()                      # D2H of the step's result
             stream.synchronize()
         host_tally[:] = t
 
@@ -304,8 +441,28 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    batch.close()
 
+    # ---- strong scaling: the same 16384 replicas split over the ranks --------------------------------------
     total_steps = float(REPLICAS_PER_GPU) * args.inner * args.steps * world
+    strong = None
+    if world > 1:
+        lo, hi = parallel.shard_bounds(REPLICAS_PER_GPU, rank, world)
+        sb, sgroups, _rows = make_batch(lo, hi - lo)
+        sms = timed_region(sb, sgroups, tally, args.steps, args.warmup)
+        stl = sb.split_tally(tally.cpu().numpy())
+        assert float(stl["n_replicas"].sum()) == REPLICAS_PER_GPU
+        strong = {"value": float(REPLICAS_PER_GPU) * args.inner * args.steps / (sms * 1e-3), "unit": UNIT,
+                  "ms_per_step": sms / args.steps, "replicas_total": REPLICAS_PER_GPU,
+                  "replicas_per_gpu": hi - lo, "kernel": sb.kernel_info()["kernel_name"],
+                  "replicas_resident_per_gpu": sb.kernel_info()["replicas_per_cta"] * sb.kernel_info()["ctas_per_sm"]
+                  * sb.kernel_info()["sm_count"]}
+        sb.close()
+    else:
+        strong = {"value": total_steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
+                  "replicas_total": REPLICAS_PER_GPU, "replicas_per_gpu": REPLICAS_PER_GPU,
+                  "note": "N = 1: identical to the weak-scaling run"}
+
     if rank == 0:
         value = total_steps / (ms * 1e-3)
         b_step = algorithmic_bytes_per_step(P, counters)
@@ -318,53 +475,49 @@ def run_ours(args, rank, world, local_rank):
         except (OSError, ValueError):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        ncu = {}
-        try:
-            with open(os.path.join(REPO, "profiles", "ncu_summary_r1.json")) as f:
-                ncu = json.load(f)
-        except (OSError, ValueError):
-            pass
+        traffic, traffic_src = _ncu_dram_bytes("C")
+        # The kernel keeps its hot state (class planes, lattice, list windows, nr_of_sites) in shared memory,
+        # so the roofline that bounds it is the shared-memory one; peak = LDS.128 streaming
+        # microbenchmark measured live on this GPU.  The HBM view is kept alongside under "hbm".
+        roofline = {
+            "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
+            "frac": achieved / smem_peak if smem_peak else None,
+            "peak_source": "live LDS.128 streaming microbenchmark on this GPU (kmos_b200_measure_smem_bandwidth)",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "kernel": "kb_gen_kernel<ruo2>", "kernel_ms_per_launch": kernel_ms,
+            "kernel_share_of_step": kernel_ms * args.steps / ms,
+            "algorithmic_bytes_per_launch": launch_bytes, "algorithmic_bytes_per_kmc_step": b_step,
+            "event_counters_per_step": counters,
+            "hbm": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured, burst copy)" if peaks else "fallback 6650 GB/s"},
+            "note": "algorithmic bytes are counted at the reference's data widths (SURVEY 8d); the kernel is "
+                    "latency-bound: one replica is a serial dependency chain (DESIGN.md 4.1)",
+        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(grid, args, extra={
-                # timing rule: inputs larger than L2 -- every bench step streams each replica's whole state
-                # (avail_sites image incl. the L2-resident lists, lattice, per-process arrays) through the GPU once
-                "l2": "no flush needed: the state a step touches (%d MB/GPU) exceeds the 126 MB L2"
-                      % (REPLICAS_PER_GPU * (kinfo["image_bytes_per_replica"] + 800 + 36 * 28 + 64) // 2**20),
-                "kernel": kinfo, "all_replicas_ok": status_ok, "kmc_steps_per_replica_total": steps_done}),
+            "config": workload_config(grid, args),
+            "kernel": kinfo, "checks": checks,
             "clocks": clocks,
             "e2e": {"value": total_steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(rates.nbytes), "d2h_bytes_per_step": int(host_tally.nbytes),
+                    "h2d_bytes_per_step": int(rate_rows.nbytes), "d2h_bytes_per_step": int(host_tally.nbytes),
                     "timing": "host wall clock, synchronized both sides, max over ranks"},
             "gpu_launches": 3 * args.steps,
-            # Contract shape: bound/achieved/peak/frac/traffic against the measured HBM copy bandwidth.  The
-            # kernel keeps its hot state in shared memory, so the roofline that physically bounds it is the
-            # shared-memory one -- reported alongside under "smem"; it is latency-/issue-bound in
-            # either view.
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured, burst copy)" if peaks else "fallback 6650 GB/s",
-                "traffic": ncu.get("dram_bytes_per_launch"),
-                "traffic_source": "profiles/ncu_summary_r1.json (ncu --set full of this launch shape)",
-                "kernel": "kb_smem_kernel", "kernel_ms_per_launch": kernel_ms,
-                "kernel_share_of_step": kernel_ms * args.steps / ms,
-                "algorithmic_bytes_per_launch": launch_bytes,
-                "algorithmic_bytes_per_kmc_step": b_step, "event_counters_per_step": counters,
-                "smem": {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
-                         "frac": achieved / smem_peak if smem_peak else None,
-                         "peak_source": "live LDS.128 streaming microbenchmark on this GPU "
-                                        "(kmos_b200_measure_smem_bandwidth)"},
-                "note": "algorithmic bytes are counted at the reference's data widths (SURVEY 8d); the kernel is "
-                        "latency-/issue-bound: one replica is a serial dependency chain (DESIGN.md 4.1)",
-            },
+            "roofline": roofline,
+            "strong": strong,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if cfg_counters is not None:
+            head = {"config": "C", "workload": CONFIGS[2][1], "model": MODEL, "lattice": SIZE,
+                    "replicas": REPLICAS_PER_GPU, "kmc_steps_per_launch": args.inner, "kernel": kinfo["kernel_name"],
+                    "replicas_per_cta": kinfo["replicas_per_cta"], "value": value, "unit": UNIT,
+                    "ms_per_launch": kernel_ms, "all_replicas_ok": status_ok,
+                    "roofline": {k: roofline[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic",
+                                                          "traffic_source", "algorithmic_bytes_per_kmc_step")}}
+            line["configs"] = measure_configs(cfg_counters, head, local_rank, smem_peak, hbm_peak)
         _emit(line)
-    batch.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -377,6 +530,7 @@ def main():
     ap.add_argument("--inner", type=int, default=5000, help="kMC steps per replica per bench step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=800000, help="kMC steps per replica of the CPU sample")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other four BASELINE configurations")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

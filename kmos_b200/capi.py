@@ -18,6 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 OK = 0
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SMEM, KERNEL_WARP_HBM, KERNEL_GENERATED = 0, 1, 2, 3, 4
+BACKEND_LOCAL_SMART, BACKEND_LAT_INT, BACKEND_OTF = 0, 1, 2
 REPLICA_OK, REPLICA_DEADLOCK, REPLICA_SPECIES_MISMATCH, REPLICA_CAPACITY, REPLICA_BAD_MODEL = range(5)
 
 

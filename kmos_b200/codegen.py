@@ -28,6 +28,7 @@ import hashlib
 import os
 import subprocess
 import sys
+import threading
 
 import numpy as np
 
@@ -309,10 +310,15 @@ def _skeleton_digest():
     return hsh
 
 
+def _extra_defs():
+    """-D switches for kernel experiments (KMOS_B200_GEN_DEFS="KB_GEN_X KB_GEN_Y"); part of the cache key."""
+    return ["-D" + d for d in os.environ.get("KMOS_B200_GEN_DEFS", "").split()]
+
+
 def _so_path(src, info, out_dir):
     hsh = _skeleton_digest()
     hsh.update(src.encode())
-    hsh.update(" ".join(NVCC_FLAGS).encode())
+    hsh.update(" ".join(NVCC_FLAGS + _extra_defs()).encode())
     return os.path.join(out_dir or CACHE, "proclist_%s_%s.so" % (info["name"], hsh.hexdigest()[:16]))
 
 
@@ -329,8 +335,8 @@ def build(ir, blob=None, name=None, out_dir=None, verbose=False, lpr=None):
     with open(cu, "w") as f:
         f.write(src)
     nvcc = os.environ.get("NVCC", "nvcc")
-    tmp = "%s.%d.tmp" % (so, os.getpid())
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", CSRC, "-o", tmp, cu]
+    tmp = "%s.%d.%d.tmp" % (so, os.getpid(), threading.get_ident())
+    cmd = [nvcc] + NVCC_FLAGS + _extra_defs() + (["-Xptxas", "-v"] if verbose else []) + ["-I", CSRC, "-o", tmp, cu]
     subprocess.check_call(cmd)
     os.replace(tmp, so)
     return so

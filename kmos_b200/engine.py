@@ -5,6 +5,7 @@ Mirrors, batched, what ``kmos.run.KMC_Model`` does with the f2py module (kmos/ru
 integ_rates / occupation, derive TOFs.  All arrays carry a leading replica axis.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -47,9 +48,12 @@ class Model(object):
 
 class Batch(object):
     def __init__(self, model, n_replicas, size, device=0, seeds=None, replica_ids=None, rates=None, lut=None,
-                 kernel=capi.KERNEL_AUTO, init=True, layer=None, proclist=None):
-        """proclist: path of the model's generated proclist module (kmos_b200.codegen.build), "auto" to use the
-        cached build of this model if there is one, "build" to generate + compile it now, or None."""
+                 kernel=capi.KERNEL_AUTO, init=True, layer=None, proclist="auto", lpr=None):
+        """proclist: the model's exporter-generated CUDA proclist (kmos_b200.codegen): a module path, "auto"
+        (default: the cached build of this model, compiled now if there is none and nvcc is on the PATH; models
+        or geometries the generator declines stay on the table interpreter), "build" (generate + compile, errors
+        are raised) or None (table interpreter only).  lpr: lanes per replica for "auto"/"build" (default: the
+        generator's choice)."""
         self.L = capi.lib()
         self.model = model
         self.R = int(n_replicas)
@@ -65,8 +69,12 @@ class Batch(object):
         self.ncells = self.volume // model.spuck
         self.layer = model.default_layer if layer is None else int(layer)
         self.proclist = None
-        if proclist:
-            self.attach_proclist(proclist)
+        if kernel == capi.KERNEL_GENERATED and proclist in (None, "auto"):
+            proclist = "build"
+        if proclist and model.backend == capi.BACKEND_LOCAL_SMART and model.ir is not None:
+            self.attach_proclist(proclist, lpr)
+        elif proclist and proclist not in ("auto", "build"):
+            self.attach_proclist(proclist, lpr)
         if kernel != capi.KERNEL_AUTO:
             self.select_kernel(kernel)
         self.set_seeds(np.arange(self.R, dtype=np.uint64) if seeds is None else seeds, replica_ids)
@@ -78,22 +86,28 @@ class Batch(object):
             self.init_state()
 
     # ---- setup -----------------------------------------------------------------------------------------
-    def attach_proclist(self, proclist="auto"):
+    def attach_proclist(self, proclist="auto", lpr=None):
         """Attach the model's exporter-generated CUDA proclist (kmos_b200_batch_attach_proclist).  Returns the
-        module path, or None when "auto" finds no cached build or the generator declines the model."""
+        module path, or None when "auto" has nothing to attach: the generator declines the model, there is no
+        cached build and no compiler, or the module declines this lattice geometry."""
+        import shutil
         from . import codegen, devtables
         path = proclist
         if proclist in ("auto", "build"):
             try:
-                if proclist == "build":
-                    path = codegen.build(self.model.ir, self.model.blob)
-                else:
-                    path = codegen.find_built(self.model.ir, self.model.blob)
+                path = codegen.find_built(self.model.ir, self.model.blob, lpr=lpr)
+                if path is None and (proclist == "build" or shutil.which(os.environ.get("NVCC", "nvcc"))):
+                    path = codegen.build(self.model.ir, self.model.blob, lpr=lpr)
             except devtables.Unsupported:
+                if proclist == "build":
+                    raise
                 path = None
             if path is None:
                 return None
-        capi.check(self.L.kmos_b200_batch_attach_proclist(self.h, str(path).encode()))
+        rc = self.L.kmos_b200_batch_attach_proclist(self.h, str(path).encode())
+        if rc != 0 and proclist == "auto":
+            return None  # e.g. a lattice smaller than twice the interaction range: the interpreter handles it
+        capi.check(rc)
         self.proclist = path
         return path
 

@@ -16,7 +16,13 @@ def shard_bounds(n_replicas, rank, world):
 
 
 def shard_of_replica(n_replicas, world, r):
-    return min(world - 1, (r * world) // n_replicas) if n_replicas >= world else r % world
+    """Rank whose shard_bounds block holds replica r: the smallest k with (n_replicas*(k+1))//world > r."""
+    k = (r * world) // n_replicas if n_replicas > 0 else 0
+    while k + 1 < world and (n_replicas * (k + 1)) // world <= r:
+        k += 1
+    while k > 0 and (n_replicas * k) // world > r:
+        k -= 1
+    return k
 
 
 def global_seeds(n_total, base_seed=17):
@@ -24,12 +30,31 @@ def global_seeds(n_total, base_seed=17):
     return (np.arange(n_total, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(base_seed))
 
 
-def all_reduce_tallies(tally, group=None):
+def count_columns(n_proc, n_occ):
+    """Columns of a tally row that are event / step / replica *counts* (kmos_b200_reduce_tallies layout:
+    procstat[P], integ_rates[P], occupation[n_occ], kmc_time, kmc_steps, n_replicas)."""
+    return list(range(n_proc)) + [2 * n_proc + n_occ + 1, 2 * n_proc + n_occ + 2]
+
+
+def all_reduce_tallies(tally, group=None, count_cols=None):
     """Sum a per-group tally tensor ([n_groups, words] float64, device or CPU) over all ranks, in place.
-    Counts (procstat, kmc_steps, n_replicas) are integers stored in doubles: exact below 2**53."""
+
+    count_cols: the columns holding counts (count_columns): they travel as an int64 all-reduce --
+    exact for any total -- and the float64 sums (integ_rates, occupation, kmc_time) as a second one.  Without
+    it everything travels as float64 (counts stay exact below 2**53)."""
+    import torch
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return tally
+    if count_cols is None:
         dist.all_reduce(tally, op=dist.ReduceOp.SUM, group=group)
+        return tally
+    t2 = tally.view(-1, tally.shape[-1])
+    idx = torch.as_tensor(count_cols, dtype=torch.long, device=tally.device)
+    counts = t2.index_select(1, idx).round().to(torch.int64)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(tally, op=dist.ReduceOp.SUM, group=group)
+    t2.index_copy_(1, idx, counts.to(torch.float64))
     return tally
 
 

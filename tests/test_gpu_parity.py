@@ -33,18 +33,50 @@ SMEM_CASES = [
 ]
 
 
+KINDS = {"smem": capi.KERNEL_SMEM, "generic": capi.KERNEL_GENERIC, "warp_hbm": capi.KERNEL_WARP_HBM,
+         "generated": capi.KERNEL_GENERATED}
+
+
 @pytest.mark.parametrize("name,size,R,chunks", SMEM_CASES)
-@pytest.mark.parametrize("kernel", ["smem", "generic", "warp_hbm"])
+@pytest.mark.parametrize("kernel", ["generated", "smem", "generic", "warp_hbm"])
 def test_local_smart_parity(name, size, R, chunks, kernel):
+    """Every local_smart fixture on every kernel that takes it; "generated" = the exporter-emitted per-model
+    module (kmos_b200/codegen.py), lane-group width chosen by the generator."""
     engine = _engine()
     ir, blob, info = load_model(name)
     rates, lut, seeds = make_inputs(ir, info, R, seed=len(name))
     model = engine.Model(ir=ir, blob=blob, info=info)
-    kind = {"smem": capi.KERNEL_SMEM, "generic": capi.KERNEL_GENERIC, "warp_hbm": capi.KERNEL_WARP_HBM}[kernel]
+    kind = KINDS[kernel]
     batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=kind)
     assert batch.kernel_info()["kernel_name"] == kernel
     gen = run_oracles(blob, size, rates, lut, seeds, chunks)
     compare_batch(batch, next(gen), avail_replicas=range(min(R, 3)))
+    for n, oracles in zip(chunks, gen):
+        batch.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(0, R - 1))
+    batch.close()
+
+
+@pytest.mark.parametrize("lpr", [8, 16, 32])
+@pytest.mark.parametrize("name,size,R,chunks", [
+    ("ruo2_local_smart", [20, 20], 7, [3000, 3000]),   # 7 replicas: the last team of 2 / 4 is incomplete
+    ("ruo2_local_smart", [5, 7], 9, [3000, 3000]),
+    ("zgb_local_smart", [16, 12], 13, [1000, 4000]),
+    ("pairwise_local_smart", [10, 9], 5, [2000, 2000]),
+    ("ab_local_smart", [20, 20], 33, [500, 2500]),
+    ("hop3d_local_smart", [5, 6, 5], 6, [2000]),
+])
+def test_generated_kernel_lane_group_widths(name, size, R, chunks, lpr):
+    """The generated kernel steps 32/lpr replicas per warp in lock step; every width must walk the oracle's
+    trajectory, with replica counts that leave the last team incomplete."""
+    engine = _engine()
+    ir, blob, info = load_model(name)
+    rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + lpr)
+    model = engine.Model(ir=ir, blob=blob, info=info)
+    batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=capi.KERNEL_GENERATED, lpr=lpr)
+    assert batch.kernel_info()["kernel_name"] == "generated"
+    gen = run_oracles(blob, size, rates, lut, seeds, chunks)
+    compare_batch(batch, next(gen), avail_replicas=(0,))
     for n, oracles in zip(chunks, gen):
         batch.do_steps(n)
         compare_batch(batch, oracles, avail_replicas=(0, R - 1))
@@ -202,7 +234,7 @@ def test_deadlock_is_a_status_not_a_hang():
     engine = _engine()
     ir, blob, info = load_model("mini_101_local_smart")
     model = engine.Model(ir=ir, blob=blob, info=info)
-    for kind in (capi.KERNEL_SMEM, capi.KERNEL_GENERIC):
+    for kind in (capi.KERNEL_GENERATED, capi.KERNEL_SMEM, capi.KERNEL_GENERIC):
         batch = engine.Batch(model, 4, [6, 6], rates=np.zeros((4, 2)), kernel=kind)
         batch.do_steps(100)
         assert np.all(batch.status == capi.REPLICA_DEADLOCK)
@@ -234,7 +266,7 @@ def test_species_mismatch_reports_the_reference_error_tuple():
     R, size = 6, [6, 5]
     seeds = np.arange(R, dtype=np.uint64) + np.uint64(3)
     rates = np.tile(np.array([100.0, 100.0]), (R, 1))
-    for kind in (capi.KERNEL_SMEM, capi.KERNEL_WARP_HBM, capi.KERNEL_GENERIC):
+    for kind in (capi.KERNEL_GENERATED, capi.KERNEL_SMEM, capi.KERNEL_WARP_HBM, capi.KERNEL_GENERIC):
         batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=kind)
         batch.do_steps(200)
         status, err, step, lat = batch.status, batch.error_info, batch.kmc_step, batch.lattice
@@ -268,7 +300,7 @@ def test_full_size_ruo2_batch_properties():
     rates, lut, seeds = make_inputs(ir, info, R, seed=9)
     model = engine.Model(ir=ir, blob=blob, info=info)
     batch = engine.Batch(model, R, size, seeds=seeds, rates=rates)
-    assert batch.kernel_info()["kernel_name"] == "smem"
+    assert batch.kernel_info()["kernel_name"] == "generated"
     batch.do_steps(n)
     assert np.all(batch.status == 0)
     assert np.all(batch.kmc_step == n)
@@ -297,12 +329,14 @@ def test_full_size_ruo2_batch_properties():
     assert np.all(tall["n_replicas"] == 1024) and np.all(tall["kmc_steps"] == 1024 * n)
 
 
-def test_reference_golden_trajectory_replayed_on_the_gpu():
+@pytest.mark.parametrize("handover", ["generated", "smem"])
+def test_reference_golden_trajectory_replayed_on_the_gpu(handover):
     """The reference's own known-answer trajectory (tests/test_run/ref_procs_sites_local_smart.log: 10 000
     (proc, site) events of the AB model, 20x20) is executed on the GPU through the reference's replay interface
     (model.run_proc_nr(proc, site), tests/test_run/test_run.py:51-53): every event must be enabled on the GPU
     when it is due, and lattice, nr_of_sites and both planes of avail_sites must follow the oracle replaying the
-    same log.  Afterwards the batch continues on the shared-memory kernel (canonical -> compact repack)."""
+    same log.  Afterwards the batch continues on the generated / the shared-memory kernel (canonical -> compact
+    repack)."""
     import os
     from conftest import GOLDEN
     from kmos_b200 import rates as rates_mod
@@ -334,7 +368,8 @@ def test_reference_golden_trajectory_replayed_on_the_gpu():
     gp, gs = batch.get_next_kmc_step()
     op_, os_, st = o.get_next_kmc_step()
     assert st == 0 and (int(gp[0]), int(gs[0])) == (op_, os_)
-    batch.select_kernel(capi.KERNEL_SMEM)
+    batch.select_kernel(KINDS[handover])
+    assert batch.kernel_info()["kernel_name"] == handover
     batch.do_steps(2000)
     o.do_steps(2000)
     assert np.array_equal(batch.lattice[0], o.lattice)
@@ -343,6 +378,7 @@ def test_reference_golden_trajectory_replayed_on_the_gpu():
 
 
 @pytest.mark.parametrize("name,size,kernel", [
+    ("ruo2_local_smart", [5, 7], "generated"), ("ab_local_smart", [4, 3], "generated"), ("zgb_local_smart", [6, 5], "generated"),
     ("ruo2_local_smart", [5, 7], "smem"), ("ruo2_local_smart", [5, 7], "warp_hbm"), ("ruo2_local_smart", [5, 7], "generic"),
     ("zgb_lat_int", [9, 7], "warp_hbm"), ("pairwise_otf_otf", [9, 8], "warp_hbm"), ("ab_local_smart", [4, 3], "smem"),
 ])
@@ -354,7 +390,7 @@ def test_many_small_launches_match_one_trajectory(name, size, kernel):
     ir, blob, info = load_model(name)
     R = 3
     rates, lut, seeds = make_inputs(ir, info, R, seed=5)
-    kind = {"smem": capi.KERNEL_SMEM, "generic": capi.KERNEL_GENERIC, "warp_hbm": capi.KERNEL_WARP_HBM}[kernel]
+    kind = KINDS[kernel]
     batch = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=rates, lut=lut, kernel=kind)
     assert batch.kernel_info()["kernel_name"] == kernel
     chunks = [1, 1, 2, 3, 5, 17, 300, 1, 255, 256, 257]
@@ -366,7 +402,7 @@ def test_many_small_launches_match_one_trajectory(name, size, kernel):
     batch.close()
 
 
-@pytest.mark.parametrize("kernel", ["smem", "warp_hbm"])
+@pytest.mark.parametrize("kernel", ["generated", "smem", "warp_hbm"])
 def test_epochs_with_replicas_that_stop_midway(kernel, monkeypatch):
     """A launch cut into several epochs (forced here) while some replicas dead-lock after 36 events: their
     remaining work items must pass through without touching the state, the others keep stepping."""
@@ -377,8 +413,7 @@ def test_epochs_with_replicas_that_stop_midway(kernel, monkeypatch):
     rates = np.tile(np.array([3.0, 2.0]), (R, 1))
     rates[::3, 1] = 0.0  # adsorption only: the 36 sites fill up, then nothing is available
     seeds = np.arange(R, dtype=np.uint64) + np.uint64(900)
-    kind = capi.KERNEL_SMEM if kernel == "smem" else capi.KERNEL_WARP_HBM
-    batch = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=rates, kernel=kind)
+    batch = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=rates, kernel=KINDS[kernel])
     gen = run_oracles(blob, size, rates, None, seeds, [500, 123])
     next(gen)
     for n, oracles in zip([500, 123], gen):

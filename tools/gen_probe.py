@@ -47,7 +47,7 @@ def parity():
             print("parity FAIL", name, size, repr(e)[:400], flush=True)
 
 
-def perf(cases=None):
+def perf(cases=None, kernels=("generated", "auto")):
     cases = cases or [("ruo2_local_smart", [20, 20], 16384, 5000), ("mini_101_local_smart", [20, 20], 16384, 5000),
                       ("zgb_local_smart", [64, 64], 4096, 2000), ("ab_local_smart", [20, 20], 16384, 4000),
                       ("pairwise_local_smart", [30, 30], 8192, 2000)]
@@ -55,7 +55,7 @@ def perf(cases=None):
         ir = tables.load_ir(os.path.join(REPO, "tests", "golden", "models", name + ".json"))
         m = engine.Model(ir=ir)
         rates = workloads.rates_for(name, ir, R)
-        for kern in ("generated", "auto"):
+        for kern in kernels:
             try:
                 b = engine.Batch(m, R, size, rates=rates, proclist="build" if kern == "generated" else None,
                                  kernel=capi.KERNEL_GENERATED if kern == "generated" else capi.KERNEL_AUTO)
@@ -84,3 +84,5 @@ if __name__ == "__main__":
         perf()
     if "ruo2" in what:
         perf([("ruo2_local_smart", [20, 20], 16384, 5000)])
+    if "ruo2gen" in what:
+        perf([("ruo2_local_smart", [20, 20], 16384, 5000)], kernels=("generated",))

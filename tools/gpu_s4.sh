@@ -1,0 +1,11 @@
+#!/bin/bash
+# A/B of kernel switches on the headline workload: KMOS_B200_GEN_DEFS variants, LPR from $1
+mkdir -p gpurun_out
+L=${1:-16}
+shift
+i=0
+for D in "$@"; do
+  i=$((i+1))
+  KMOS_B200_GEN_LPR=$L KMOS_B200_GEN_DEFS="$D" timeout 600 python tools/gen_probe.py ruo2gen > gpurun_out/ab_$i.log 2>&1
+  echo "== [$D]"; grep -o '"kernel": "[a-z]*", "ms": [0-9.]*, "steps_per_s": [0-9.]*' gpurun_out/ab_$i.log; grep -i "error\|fail" gpurun_out/ab_$i.log | head -3
+done
