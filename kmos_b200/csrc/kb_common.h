@@ -162,6 +162,13 @@ static inline const int32_t* kb_find_section(const int32_t* blob, int id, int* l
 // reading the header from the host copy `hblob`.
 static inline bool kb_model_view(const int32_t* hblob, int64_t n_words, const int32_t* base, KbModelView* m) {
     if (n_words < 14 || hblob[0] != KB20_MAGIC || hblob[1] != KB20_VERSION) return false;
+    // a malformed blob must not send the section pointers out of bounds: table and every section inside n_words
+    const int64_t nsec = hblob[13];
+    if (nsec < 0 || 14 + 3 * nsec > n_words) return false;
+    for (int64_t i = 0; i < nsec; ++i) {
+        const int64_t off = hblob[14 + 3 * i + 1], len = hblob[14 + 3 * i + 2];
+        if (off < 0 || len < 0 || off + len > n_words) return false;
+    }
     m->blob = base;
     m->backend = hblob[2]; m->n_species = hblob[3]; m->n_proc = hblob[4]; m->spuck = hblob[5]; m->dim = hblob[6];
     m->default_species = hblob[7] & 0xFFFF; m->null_species = (hblob[7] >> 16) - 1; m->n_layers = hblob[8]; m->default_layer = hblob[9]; m->n_routines = hblob[10];

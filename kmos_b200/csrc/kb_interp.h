@@ -389,6 +389,36 @@ struct KbInterp {
                     }
     }
 
+    // proclist.recalculate_rates_matrix (proclist_generic_subroutines.mpy:307-325) + base.reaccumulate_rates_matrix
+    // (base_otf.f90:366-387): every registered (process, site) gets the current gr_<proc> value, then every
+    // row total is re-added from scratch in memory-address order (which makes the visiting order irrelevant)
+    KB_HDN void recalculate_rates_matrix() {
+        if (m.backend != KB_BACKEND_OTF) return;
+        const int32_t zero_off[4] = {0, 0, 0, 0};
+        for (int gid = 0; gid < m.n_gr; ++gid) {
+            const int proc = m.gr[(size_t)gid * KB_GR_STRIDE + 1];
+            const size_t row = (size_t)(proc - 1) * g.ncells;
+            double* rm = r.rates_matrix + (size_t)(proc - 1) * (g.ncells + 1);
+            const int nq = r.nsites[proc - 1];
+            for (int pos = 0; pos < nq; ++pos) {
+                int cell = (int)r.p1[row + pos];
+                int base[4];
+                base[0] = cell % g.size[0]; cell /= g.size[0];
+                base[1] = cell % g.size[1]; cell /= g.size[1];
+                base[2] = cell; base[3] = 0;
+                rm[pos] = eval_gr(gid, base, zero_off);
+            }
+        }
+        for (int proc = 1; proc <= m.n_proc; ++proc) {
+            double* rm = r.rates_matrix + (size_t)(proc - 1) * (g.ncells + 1);
+            const int nq = r.nsites[proc - 1];
+            double tot = 0.0;
+            for (int pos = 0; pos < nq; ++pos) tot = KB_ADD(tot, rm[pos]);
+            rm[g.ncells] = tot;
+        }
+        update_accum_rate();
+    }
+
     // KMC_Model._set_configuration + _adjust_database (kmos/run/__init__.py:1411-1457): the lattice has
     // been overwritten by the caller; touch up x-outermost, without clearing avail_sites first.
     KB_HDN void adjust_database(int layer) {

@@ -40,6 +40,9 @@ static int set_err(int code, const std::string& msg) {
             return set_err(KMOS_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
     } while (0)
 
+struct kmos_b200_batch;
+static cudaError_t kb_h2d(kmos_b200_batch* b, void* dst, const void* src, size_t bytes);
+
 struct kmos_b200_model {
     std::vector<int32_t> blob;
     KbModelView h;  // pointers into blob (host)
@@ -101,6 +104,7 @@ struct kmos_b200_batch {
     // generated per-model kernel (kmos_b200_batch_attach_proclist)
     KbGenModule gen;
     bool gen_ok;
+    bool initialised;          // init_state / set_configuration / reload_replica has run
     KbGenPlan gp;
     uint32_t* d_gen_tab;
     uint32_t* d_gen_writes;
@@ -200,7 +204,8 @@ __device__ __forceinline__ void kb_store_replica(const KbBatchView& b, int rep, 
     b.sc[rep] = s;
 }
 
-enum { KB_MODE_STEPS = 0, KB_MODE_INIT = 1, KB_MODE_ADJUST = 2, KB_MODE_ACCUM = 3, KB_MODE_NEXT = 4, KB_MODE_RUNPROC = 5 };
+enum { KB_MODE_STEPS = 0, KB_MODE_INIT = 1, KB_MODE_ADJUST = 2, KB_MODE_ACCUM = 3, KB_MODE_NEXT = 4, KB_MODE_RUNPROC = 5,
+       KB_MODE_RECALC = 6 };
 
 template <typename idx_t>
 __global__ void kb_generic_kernel(const KbBatchView b, int mode, long long n, int layer, int only_rep,
@@ -214,6 +219,7 @@ __global__ void kb_generic_kernel(const KbBatchView b, int mode, long long n, in
     if (mode == KB_MODE_STEPS) it.do_kmc_steps(n);
     else if (mode == KB_MODE_INIT) it.init_state(layer);
     else if (mode == KB_MODE_ADJUST) it.adjust_database(layer);
+    else if (mode == KB_MODE_RECALC) it.recalculate_rates_matrix();
     else if (mode == KB_MODE_NEXT) {
         // get_next_kmc_step (proclist_generic_subroutines.mpy:85-110): the step's uniforms, no clock update,
         // and -- as in the reference -- ran_time is what selects the site
@@ -573,6 +579,16 @@ static int auto_kernel(const kmos_b200_batch* b) {
     return (b->li_ok || b->otf_ok) ? KMOS_B200_KERNEL_WARP_HBM : KMOS_B200_KERNEL_GENERIC;
 }
 
+// host -> device copy of a temporary host buffer, ordered on the batch's own (non-blocking) stream
+static cudaError_t kb_h2d(kmos_b200_batch* b, void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, b->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(b->stream);
+}
+
+static int batch_setup(kmos_b200_batch* b, kmos_b200_model* m, int32_t R, const int32_t size[3]);
+static int launch_generic(kmos_b200_batch* b, int mode, long long n, int layer, int only_rep, int32_t* io_proc, int32_t* io_site);
+
 extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32_t size[3], int32_t device,
                                       kmos_b200_batch** out) {
     if (!m || !out || R <= 0 || !size) return set_err(KMOS_B200_ERR_ARG, "batch_create: bad arguments");
@@ -580,14 +596,24 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     if (ndev == 0) return set_err(KMOS_B200_ERR_CUDA, "batch_create: no CUDA device (this engine has no CPU fallback)");
     if (device < 0 || device >= ndev) return set_err(KMOS_B200_ERR_ARG, "batch_create: bad device index");
     CU(cudaSetDevice(device));
-    kmos_b200_batch* b = new kmos_b200_batch();
+    for (int a = 0; a < m->h.dim; ++a)
+        if (size[a] <= 0) return set_err(KMOS_B200_ERR_ARG, "batch_create: bad lattice size");
+    kmos_b200_batch* b = new kmos_b200_batch();  // value-initialised: every pointer starts out null
     b->model = m; b->R = R; b->device = device;
-    for (int a = 0; a < 3; ++a) {
-        b->g.size[a] = a < m->h.dim ? size[a] : 1;
-        if (b->g.size[a] <= 0) { delete b; return set_err(KMOS_B200_ERR_ARG, "batch_create: bad lattice size"); }
+    const int rc = batch_setup(b, m, R, size);
+    if (rc != KMOS_B200_OK) {  // nothing leaks on an error path: the batch and whatever it allocated so far go
+        kmos_b200_batch_destroy(b);
+        cudaGetLastError();
+        return rc;
     }
+    *out = b;
+    return KMOS_B200_OK;
+}
+
+static int batch_setup(kmos_b200_batch* b, kmos_b200_model* m, int32_t R, const int32_t size[3]) {
+    for (int a = 0; a < 3; ++a) b->g.size[a] = a < m->h.dim ? size[a] : 1;
     long long cells = (long long)b->g.size[0] * b->g.size[1] * b->g.size[2];
-    if (cells * m->h.spuck > 0x7fffffffLL) { delete b; return set_err(KMOS_B200_ERR_ARG, "lattice too large"); }
+    if (cells * m->h.spuck > 0x7fffffffLL) return set_err(KMOS_B200_ERR_ARG, "lattice too large");
     b->g.ncells = (int)cells; b->g.volume = (int)cells * m->h.spuck;
     b->idx32 = b->g.ncells >= 65536;
     const int P = m->h.n_proc;
@@ -599,7 +625,7 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     CU(cudaEventCreate(&b->ev1));
     const size_t nblob = m->blob.size() * 4;
     CU(cudaMalloc(&b->d_blob, nblob));
-    CU(cudaMemcpy(b->d_blob, m->blob.data(), nblob, cudaMemcpyHostToDevice));
+    CU(kb_h2d(b, b->d_blob, m->blob.data(), nblob));
     kb_model_view(m->blob.data(), (int64_t)m->blob.size(), b->d_blob, &b->d);
     const size_t RP = (size_t)R * P;
     CU(cudaMalloc(&b->lattice, (size_t)R * b->lat_stride));
@@ -631,7 +657,7 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     std::vector<KbScalars> sc(R);
     memset(sc.data(), 0, sc.size() * sizeof(KbScalars));
     for (int r = 0; r < R; ++r) { sc[r].seed = 1; sc[r].replica = (uint32_t)r; }
-    CU(cudaMemcpy(b->sc, sc.data(), sc.size() * sizeof(KbScalars), cudaMemcpyHostToDevice));
+    CU(kb_h2d(b, b->sc, sc.data(), sc.size() * sizeof(KbScalars)));
     b->tally = nullptr; b->occ = nullptr; b->group_of = nullptr; b->tally_groups = 0;
     plan_smem(b);
     plan_latint(b);
@@ -645,24 +671,27 @@ extern "C" int kmos_b200_batch_create(kmos_b200_model* m, int32_t R, const int32
     if (b->smem_ok) {
         CU(cudaMalloc(&b->image, (size_t)R * b->sp.img_bytes));
         CU(cudaMalloc(&b->d_spec, b->spec.size() * 4));
-        CU(cudaMemcpy(b->d_spec, b->spec.data(), b->spec.size() * 4, cudaMemcpyHostToDevice));
+        CU(kb_h2d(b, b->d_spec, b->spec.data(), b->spec.size() * 4));
     }
     b->kernel = auto_kernel(b);
-    *out = b;
+    // the set-up above used the legacy default stream; the batch's own stream is non-blocking and does not
+    // order after it, so everything lands before the first call that uses the stream
+    CU(cudaDeviceSynchronize());
     return KMOS_B200_OK;
 }
 
 extern "C" void kmos_b200_batch_destroy(kmos_b200_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    cudaStreamSynchronize(b->stream);
+    if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_blob); cudaFree(b->lattice); cudaFree(b->p1); cudaFree(b->p2); cudaFree(b->nsites);
     cudaFree(b->rates); cudaFree(b->integ); cudaFree(b->accum); cudaFree(b->procstat); cudaFree(b->sc);
     cudaFree(b->rates_matrix); cudaFree(b->accum_proc); cudaFree(b->lut); cudaFree(b->tally); cudaFree(b->occ); cudaFree(b->group_of); cudaFree(b->image); cudaFree(b->d_spec); cudaFree(b->d_sched);
     cudaFree(b->d_gen_tab); cudaFree(b->d_gen_writes); cudaFree(b->d_gen_dev); cudaFree(b->gen_image);
     if (b->gen.handle) dlclose(b->gen.handle);
-    cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
-    cudaStreamDestroy(b->own_stream);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
 }
 
@@ -747,7 +776,7 @@ static int edit_scalars(kmos_b200_batch* b, void (*fn)(KbScalars&, int, const vo
     std::vector<KbScalars> sc(b->R);
     CU(cudaMemcpy(sc.data(), b->sc, sc.size() * sizeof(KbScalars), cudaMemcpyDeviceToHost));
     for (int r = 0; r < b->R; ++r) fn(sc[r], r, arg);
-    CU(cudaMemcpy(b->sc, sc.data(), sc.size() * sizeof(KbScalars), cudaMemcpyHostToDevice));
+    CU(kb_h2d(b, b->sc, sc.data(), sc.size() * sizeof(KbScalars)));
     return KMOS_B200_OK;
 }
 
@@ -782,10 +811,11 @@ extern "C" int kmos_b200_set_rate_const(kmos_b200_batch* b, int32_t replica, int
     CU(cudaSetDevice(b->device));
     CU(cudaStreamSynchronize(b->stream));
     if (replica >= 0) {
-        CU(cudaMemcpy(b->rates + (size_t)replica * P + proc - 1, &rate, 8, cudaMemcpyHostToDevice));
+        CU(kb_h2d(b, b->rates + (size_t)replica * P + proc - 1, &rate, 8));
     } else {
         std::vector<double> col(b->R, rate);
-        CU(cudaMemcpy2D(b->rates + proc - 1, (size_t)P * 8, col.data(), 8, 8, b->R, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy2DAsync(b->rates + proc - 1, (size_t)P * 8, col.data(), 8, 8, b->R, cudaMemcpyHostToDevice, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
     }
     return KMOS_B200_OK;
 }
@@ -801,6 +831,9 @@ extern "C" int kmos_b200_set_otf_lut(kmos_b200_batch* b, const double* lut) {
     if (b->model->h.backend != KB_BACKEND_OTF) return set_err(KMOS_B200_ERR_ARG, "set_otf_lut: not an otf model");
     CU(cudaSetDevice(b->device));
     CU(cudaMemcpyAsync(b->lut, lut, (size_t)b->R * b->model->h.lut_total * 8, cudaMemcpyHostToDevice, b->stream));
+    // events already registered keep the rate they were added with: refresh every entry and re-add the rows,
+    // as KMC_Model.set_rate_constants does (proclist.recalculate_rates_matrix)
+    if (b->initialised) return launch_generic(b, KB_MODE_RECALC, 0, 0, -1, nullptr, nullptr);
     return KMOS_B200_OK;
 }
 
@@ -848,8 +881,11 @@ static int ensure_compact(kmos_b200_batch* b, int kind = 0) {
     return KMOS_B200_OK;
 }
 
+static int launch_generic(kmos_b200_batch* b, int mode, long long n, int layer, int only_rep) {
+    return launch_generic(b, mode, n, layer, only_rep, nullptr, nullptr);
+}
 static int launch_generic(kmos_b200_batch* b, int mode, long long n, int layer, int only_rep,
-                          int32_t* io_proc = nullptr, int32_t* io_site = nullptr) {
+                          int32_t* io_proc, int32_t* io_site) {
     CU(cudaSetDevice(b->device));
     int rc = ensure_canonical(b);
     if (rc) return rc;
@@ -865,6 +901,7 @@ static int launch_generic(kmos_b200_batch* b, int mode, long long n, int layer, 
 extern "C" int kmos_b200_init_state(kmos_b200_batch* b, int32_t layer) {
     const KbModelView& m = b->model->h;
     if (layer < 0 || layer >= m.n_layers || m.init[2 * layer] < 0) return set_err(KMOS_B200_ERR_ARG, "init_state: bad layer");
+    b->initialised = true;
     return launch_generic(b, KB_MODE_INIT, 0, layer, -1);
 }
 
@@ -882,7 +919,8 @@ extern "C" int kmos_b200_set_configuration(kmos_b200_batch* b, int32_t replica, 
             if (s >= m.n_species) return set_err(KMOS_B200_ERR_ARG, "set_configuration: species id out of range");
             lat[(size_t)(r - r0) * b->lat_stride + i] = s < 0 ? KB_NULL_SPECIES : (uint8_t)s;
         }
-    CU(cudaMemcpy(b->lattice + (size_t)r0 * b->lat_stride, lat.data(), lat.size(), cudaMemcpyHostToDevice));
+    CU(kb_h2d(b, b->lattice + (size_t)r0 * b->lat_stride, lat.data(), lat.size()));
+    b->initialised = true;
     return launch_generic(b, KB_MODE_ADJUST, 0, layer, replica);
 }
 
@@ -1260,17 +1298,17 @@ extern "C" int kmos_b200_reload_replica(kmos_b200_batch* b, int32_t replica, con
     if (rc) return rc;
     CU(cudaStreamSynchronize(b->stream));
     std::vector<double> zeros(P, 0.0);
-    CU(cudaMemcpy(b->lattice + (size_t)replica * b->lat_stride, lat.data(), lat.size(), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy((char*)b->p1 + (size_t)replica * b->plane_bytes, h1.data(), b->plane_bytes, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy((char*)b->p2 + (size_t)replica * b->plane_bytes, h2.data(), b->plane_bytes, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(b->nsites + (size_t)replica * P, nr_of_sites, (size_t)P * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(b->procstat + (size_t)replica * P, procstat, (size_t)P * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(b->integ + (size_t)replica * P, integ_rates ? integ_rates : zeros.data(), (size_t)P * 8, cudaMemcpyHostToDevice));
+    CU(kb_h2d(b, b->lattice + (size_t)replica * b->lat_stride, lat.data(), lat.size()));
+    CU(kb_h2d(b, (char*)b->p1 + (size_t)replica * b->plane_bytes, h1.data(), b->plane_bytes));
+    CU(kb_h2d(b, (char*)b->p2 + (size_t)replica * b->plane_bytes, h2.data(), b->plane_bytes));
+    CU(kb_h2d(b, b->nsites + (size_t)replica * P, nr_of_sites, (size_t)P * 4));
+    CU(kb_h2d(b, b->procstat + (size_t)replica * P, procstat, (size_t)P * 8));
+    CU(kb_h2d(b, b->integ + (size_t)replica * P, integ_rates ? integ_rates : zeros.data(), (size_t)P * 8));
     KbScalars sc;
     CU(cudaMemcpy(&sc, b->sc + replica, sizeof sc, cudaMemcpyDeviceToHost));
     sc.kmc_time = kmc_time; sc.kmc_step = kmc_step; sc.kmc_time_step = 0.0; sc.status = KB_OK;
     for (int i = 0; i < 5; ++i) sc.err[i] = 0;
-    CU(cudaMemcpy(b->sc + replica, &sc, sizeof sc, cudaMemcpyHostToDevice));
+    CU(kb_h2d(b, b->sc + replica, &sc, sizeof sc));
     return launch_generic(b, KB_MODE_ACCUM, 0, 0, replica);
 }
 

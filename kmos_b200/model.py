@@ -29,9 +29,12 @@ class _Namespace(object):
 
 class KMC_Model(object):
     def __init__(self, model, size=20, n_replicas=1, seeds=None, parameters=None, device=0, kernel=capi.KERNEL_AUTO,
-                 random_seed=1, mu=rates_mod.standin_mu, cache_file=None):
+                 random_seed=1, mu=None, cache_file=None):
         """model: path of a rule-table JSON (what the exporter hook writes) or a parsed IR dict.
-        parameters: dict of overrides, or a list of R dicts (one parameter point per replica)."""
+        parameters: dict of overrides, or a list of R dicts (one parameter point per replica).
+        mu: chemical potentials for ``mu_<gas>`` tokens: a ``kmos.species``-compatible provider or a callable
+        (gas, T, p) -> eV.  Default: the reference's kmos.species if importable, else the closed-form stand-in
+        of kmos_b200.rates with a MuStandinWarning (rate constants then differ from the reference's)."""
         self.ir = tables.load_ir(model) if isinstance(model, str) else model
         self.model = engine.Model(ir=self.ir)
         dim = self.ir["model_dimension"]
@@ -259,7 +262,11 @@ class KMC_Model(object):
     def put(self, site, new_species, replica=0):
         """Put `new_species` (name or id) on site [x, y, z, n] and re-adjust the book-keeping
         (kmos/run/__init__.py:1243-1283 + _adjust_database)."""
-        x, y, z, n = (list(site) + [0, 0, 0, 1])[:4] if len(site) < 4 else site
+        if len(site) != 4:
+            raise ValueError("put: site must be [x, y, z, n] (n = 1-based site type), as in the reference")
+        x, y, z, n = (int(v) for v in site)
+        if not 1 <= n <= self.model.spuck:
+            raise ValueError("put: site type n=%d outside 1..%d" % (n, self.model.spuck))
         sp = self.species_names.index(new_species) if isinstance(new_species, str) else int(new_species)
         cfg = self._get_configuration(replica)
         cfg[x % self.size[0], y % self.size[1], z % self.size[2], n - 1] = sp

@@ -8,11 +8,16 @@ nor network, so this module restates just enough of that to turn the rate expres
 model fixtures into the ``rates[R][P]`` matrix that both the oracle and the CUDA engine consume.
 Because both sides are fed the same numbers, parity does not depend on this file.
 
-``standin_mu`` replaces the JANAF interpolation by a closed form (documented stand-in).
+Chemical potentials: ``mu`` may be a callable ``(gas, T, p) -> eV``, a ``kmos.species``-compatible provider
+(attribute ``<gas>`` with a ``mu(T, p)`` method), or None.  None means "what the reference would use": the
+reference's own ``kmos.species`` when it is importable (JANAF tables), otherwise the closed-form stand-in
+``standin_mu`` **with a warning** -- the synthetic benchmark workloads pass ``standin_mu`` explicitly (SURVEY
+8d).  A gas without a table gives 0 with a warning, as in the reference (kmos/__init__.py:157-160).
 """
 import math
 import re
 import tokenize
+import warnings
 from io import StringIO
 
 # CODATA 2010 values as in kmos/units.py:26-36
@@ -46,10 +51,19 @@ _MU_STANDIN = {
 }
 
 
+class MuStandinWarning(UserWarning):
+    pass
+
+
 def standin_mu(name, T, p):
-    """Chemical potential stand-in in eV: linear-in-T entropy term + k_B T ln p (T in K, p in bar)."""
+    """Chemical potential stand-in in eV: linear-in-T entropy term + k_B T ln p (T in K, p in bar).
+    NOT the JANAF value the reference uses; a gas without an entry gives 0 with a warning, as the reference
+    does for a species without a table."""
     key = name if name in _MU_STANDIN else name + "gas"
-    a, b = _MU_STANDIN.get(key, (0.0, -2.0e-3))
+    if key not in _MU_STANDIN:
+        warnings.warn("No chemical-potential table for %s: setting it to zero" % name, MuStandinWarning)
+        return 0.0
+    a, b = _MU_STANDIN[key]
     T = float(T)
     return a + b * (T - 298.15) * 0.5 + b * T * 0.5 * math.log(max(T, 1.0) / 298.15) \
         + _KB_EV * T * math.log(float(p))
@@ -62,7 +76,38 @@ def _string2symbols(s):
     return out
 
 
-def evaluate_rate_expression(rate_expr, parameters=None, mu=standin_mu, masses=ATOMIC_MASSES):
+def _reference_species():
+    """kmos.species of an importable reference installation (JANAF tables), or None."""
+    try:
+        from kmos import species  # noqa: WPS433 -- optional: only where the reference is installed
+        return species
+    except Exception:
+        return None
+
+
+def resolve_mu(mu):
+    """-> callable (gas, T, p) -> eV for any accepted `mu` argument (see the module docstring)."""
+    if callable(mu):
+        return mu
+    provider = mu if mu is not None else _reference_species()
+    if provider is not None:
+        def from_provider(name, T, p):
+            if not hasattr(provider, name):
+                warnings.warn("No JANAF table assigned for %s: setting chemical potential to zero" % name,
+                              MuStandinWarning)
+                return 0.0
+            return float(getattr(provider, name).mu(T, p))
+        return from_provider
+
+    def warned(name, T, p):
+        warnings.warn("mu_%s evaluated with the closed-form stand-in (kmos_b200.rates.standin_mu), not with the "
+                      "JANAF tables of kmos.species: pass mu=<provider> for the reference's rate constants" % name,
+                      MuStandinWarning, stacklevel=3)
+        return standin_mu(name, T, p)
+    return warned
+
+
+def evaluate_rate_expression(rate_expr, parameters=None, mu=None, masses=ATOMIC_MASSES):
     """Mirror of kmos.evaluate_rate_expression (kmos/__init__.py:67-189).
 
     ``parameters``: {name: {"value": v}} or {name: v}.  Same textual substitution + eval so that the
@@ -88,7 +133,11 @@ def evaluate_rate_expression(rate_expr, parameters=None, mu=standin_mu, masses=A
             replaced.append((i, "%s" % sum(masses[s] for s in _string2symbols(species_name))))
         elif token.startswith("mu_"):
             species_name = "_".join(token.split("_")[1:])
-            replaced.append((i, repr(mu(species_name, pdict["T"], pdict["p_%s" % species_name]))))
+            if "T" not in pdict:
+                raise KeyError('Need "T" in parameters to evaluate chemical potential.')
+            if "p_%s" % species_name not in pdict:
+                raise KeyError('Need "p_%s" in parameters to evaluate chemical potential.' % species_name)
+            replaced.append((i, repr(resolve_mu(mu)(species_name, pdict["T"], pdict["p_%s" % species_name]))))
         elif token in pdict:
             s = str(pdict[token])
             for unit in UNIT_KEYS:

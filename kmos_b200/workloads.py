@@ -17,7 +17,8 @@ def ruo2_grid(ir, n_T=16, n_p=16, seeds=64, T_range=(450.0, 650.0), p_range=(1e-
     points = []
     for T in Ts:
         for p in ps:
-            points.append(rates_mod.model_rates(ir, {"T": float(T), "p_COgas": float(p), "p_O2gas": float(p_O2)}))
+            points.append(rates_mod.model_rates(ir, {"T": float(T), "p_COgas": float(p), "p_O2gas": float(p_O2)},
+                                                mu=rates_mod.standin_mu))
     points = np.asarray(points)
     rates = np.repeat(points, seeds, axis=0)
     group_of = np.repeat(np.arange(len(points), dtype=np.int32), seeds)
@@ -26,7 +27,7 @@ def ruo2_grid(ir, n_T=16, n_p=16, seeds=64, T_range=(450.0, 650.0), p_range=(1e-
 
 def zgb_grid(ir, n_y=64, seeds=64):
     ys = 0.30 + 0.25 * (np.arange(n_y) / max(n_y - 1, 1))
-    points = np.asarray([rates_mod.model_rates(ir, {"yCO": float(y)}) for y in ys])
+    points = np.asarray([rates_mod.model_rates(ir, {"yCO": float(y)}, mu=rates_mod.standin_mu) for y in ys])
     return np.repeat(points, seeds, axis=0), np.repeat(np.arange(n_y, dtype=np.int32), seeds), {"yCO": ys.tolist()}
 
 
@@ -39,7 +40,7 @@ def rates_for(name, ir, R):
         seeds = max(R // 64, 1)
         r, _g, _d = zgb_grid(ir, seeds=seeds)
     elif ir.get("process_defs"):
-        r = np.asarray([rates_mod.model_rates(ir)])
+        r = np.asarray([rates_mod.model_rates(ir, mu=rates_mod.standin_mu)])
     else:  # fixtures parsed from committed Fortran carry no rate expressions: unit rate constants
         r = np.ones((1, len(ir["procs"])))
     reps = -(-R // len(r))

@@ -525,6 +525,31 @@ void kmos_oracle_set_lut(oracle_t *o, const double *lut) {
     if (o->lut && o->lut_total > 0) memcpy(o->lut, lut, (size_t)o->lut_total * 8);
 }
 
+/* proclist.recalculate_rates_matrix (proclist_generic_subroutines.mpy:307-325): for every process, x outermost,
+ * every site that can do it gets the current gr_<proc> value; then base.reaccumulate_rates_matrix
+ * (base_otf.f90:366-387) re-adds every row from scratch in memory-address order. */
+void kmos_oracle_recalculate_rates_matrix(oracle_t *o) {
+    if (o->backend != BACKEND_OTF) return;
+    static const int32_t zero_off[4] = {0, 0, 0, 0};
+    for (int gid = 0; gid < o->n_gr; ++gid) {
+        const int proc = o->gr[(size_t)gid * GR_STRIDE + 1];
+        for (int i = 0; i < o->size[0]; ++i)
+            for (int j = 0; j < o->size[1]; ++j)
+                for (int k = 0; k < o->size[2]; ++k) {
+                    int s1[4] = {i, j, k, 1}, base[4] = {i, j, k, 0};
+                    const int site = lattice2nr(o, s1);
+                    if (can_do(o, proc, site)) update_rates_matrix(o, proc, site, eval_gr(o, gid, base, zero_off));
+                }
+    }
+    for (int proc = 1; proc <= o->n_proc; ++proc) {
+        RM(o, proc, o->volume + 1) = 0.0;
+        for (int memadd = 1; memadd <= o->volume; ++memadd) {
+            if (AV1(o, proc, memadd) > 0) RM(o, proc, o->volume + 1) = RM(o, proc, o->volume + 1) + RM(o, proc, memadd);
+            else RM(o, proc, memadd) = 0.0;
+        }
+    }
+}
+
 /* touchup of every cell in the reference's loop order (proclist_generic_subroutines.mpy:279-299) */
 static void touchup_all(oracle_t *o, int layer) {
     int rid = o->init[2 * layer + 1], dummy = 0;

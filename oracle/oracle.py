@@ -38,6 +38,8 @@ def lib():
         L.kmos_oracle_seed.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32]
         L.kmos_oracle_set_rates.argtypes = [C.c_void_p, f64p]
         L.kmos_oracle_set_lut.argtypes = [C.c_void_p, f64p]
+        L.kmos_oracle_recalculate_rates_matrix.argtypes = [C.c_void_p]
+        L.kmos_oracle_recalculate_rates_matrix.restype = None
         L.kmos_oracle_init_state.argtypes = [C.c_void_p, C.c_int]
         L.kmos_oracle_set_configuration.argtypes = [C.c_void_p, i32p, C.c_int]
         L.kmos_oracle_do_steps.argtypes = [C.c_void_p, C.c_int64]
@@ -124,6 +126,10 @@ class Oracle(object):
 
     def set_lut(self, lut):
         self.L.kmos_oracle_set_lut(self.h, np.ascontiguousarray(lut, dtype=np.float64))
+
+    def recalculate_rates_matrix(self):
+        """proclist.recalculate_rates_matrix: what KMC_Model.set_rate_constants ends with for otf models."""
+        self.L.kmos_oracle_recalculate_rates_matrix(self.h)
 
     def set_configuration(self, species):
         s = np.ascontiguousarray(species, dtype=np.int32)

@@ -54,3 +54,36 @@ def test_side_by_side_with_the_reference_implementation():
             assert ours == pytest.approx(ref, rel=1e-13), (name, p["name"], expr)
             checked += 1
     assert checked >= 40
+
+
+def test_mu_tokens_use_a_provider_or_warn_about_the_standin():
+    """a drop-in KMC_Model must not silently replace the JANAF chemical potentials.  `mu` accepts a
+    kmos.species-compatible provider; without one (and without an importable reference) the closed-form stand-in
+    is used *with a warning*; a gas without a table evaluates to 0 with a warning, as in the reference
+    (kmos/__init__.py:128-160)."""
+    import warnings
+
+    import pytest
+
+    params = {"T": {"value": 500.0}, "p_COgas": {"value": 2.0}, "p_Xegas": {"value": 1.0}}
+
+    class Gas(object):
+        def mu(self, T, p):
+            return -1.25 + 1e-3 * T * p
+
+    class Provider(object):
+        COgas = Gas()
+
+    got = rates.evaluate_rate_expression("exp(mu_COgas)", params, mu=Provider())
+    assert got == pytest.approx(math.exp(-1.25 + 1e-3 * 500.0 * 2.0), rel=1e-15)
+    with pytest.warns(rates.MuStandinWarning, match="No JANAF table"):
+        assert rates.evaluate_rate_expression("1 + mu_Xegas", params, mu=Provider()) == 1.0
+    if rates._reference_species() is None:  # the GPU box and this container: no kmos installation
+        with pytest.warns(rates.MuStandinWarning, match="stand-in"):
+            v = rates.evaluate_rate_expression("mu_COgas", params)
+        assert v == rates.standin_mu("COgas", 500.0, 2.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # the explicit stand-in (synthetic workloads) stays silent
+        rates.evaluate_rate_expression("mu_COgas", params, mu=rates.standin_mu)
+    with pytest.raises(KeyError):
+        rates.evaluate_rate_expression("mu_O2gas", params, mu=rates.standin_mu)
