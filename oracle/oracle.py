@@ -172,6 +172,12 @@ class Oracle(object):
     accum_rates = property(lambda self: self._get("accum_rates", self.n_proc, np.float64))
     avail_sites = property(lambda self: self._get("avail_sites", (self.n_proc, self.volume, 2), np.int32))
     occupation = property(lambda self: self._get("occupation", (self.n_species, self.spuck), np.float64))
+
+    def rates_matrix_row(self, proc):
+        """otf: rates_matrix(proc, 1..volume+1) (last entry: the row total)."""
+        out = np.zeros(self.volume + 1)
+        self.L.kmos_oracle_get_rates_matrix_row(self.h, int(proc), out)
+        return out
     counters = property(lambda self: dict(zip(("n_rs", "n_chk", "n_del", "n_gs", "n_add", "n_upd"),
                                               self._get("counters", 6, np.int64).tolist())))
 
