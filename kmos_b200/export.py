@@ -21,11 +21,42 @@ def export_tables(export_dir, backend=None, project=None):
     ir = fortran_ir.parse_export_dir(export_dir, backend)
     if project is not None:
         ir.update(project_meta(project))
+    ir.update(lattice_geometry(export_dir))
     blob, info = tables.build_blob(ir)
     with open(os.path.join(export_dir, "model_tables.json"), "w") as f:
         json.dump(ir, f, separators=(",", ":"), sort_keys=True)
     blob.tofile(os.path.join(export_dir, "model_tables.bin"))
+    # the model's proclist as specialised CUDA, next to the proclist.f90 it mirrors (local_smart models the
+    # generator takes; the others run on the table interpreter / the warp kernels)
+    if ir["backend"] == "local_smart":
+        from . import codegen, devtables
+        try:
+            path, _inf = codegen.write_source(ir, export_dir, blob)
+            info["proclist_cu"] = path
+        except devtables.Unsupported as e:
+            info["proclist_cu"] = None
+            info["proclist_cu_declined"] = str(e)
     return ir, blob, info
+
+
+def lattice_geometry(export_dir):
+    """unit_cell_size / site_positions from the generated lattice.f90 (kmos/io/__init__.py:650-700): only the
+    front-end uses them (KMC_Model.cell_size, get_atoms), the step loop does not."""
+    import re
+    path = os.path.join(export_dir, "lattice.f90")
+    if not os.path.exists(path):
+        return {}
+    cell = [[0.0] * 3 for _ in range(3)]
+    pos = {}
+    with open(path) as f:
+        for line in f:
+            m = re.match(r"\s*unit_cell_size\((\d), (\d)\) = ([-+.\deEdD]+)", line)
+            if m:
+                cell[int(m.group(1)) - 1][int(m.group(2)) - 1] = float(m.group(3).lower().replace("d", "e"))
+            m = re.match(r"\s*site_positions\((\d+),:\) = \(/(.*)/\)", line)
+            if m:
+                pos[int(m.group(1))] = [float(x.lower().replace("d", "e")) for x in m.group(2).split(",")]
+    return {"unit_cell_size": cell, "site_positions": [pos[k] for k in sorted(pos)]}
 
 
 def project_meta(pt):

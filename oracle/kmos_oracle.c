@@ -638,6 +638,7 @@ int kmos_oracle_nproc(const oracle_t *o) { return o->n_proc; }
 int kmos_oracle_status(const oracle_t *o, int32_t err[5]) { if (err) memcpy(err, o->err, sizeof o->err); return o->status; }
 double kmos_oracle_kmc_time(const oracle_t *o) { return o->kmc_time; }
 double kmos_oracle_kmc_time_step(const oracle_t *o) { return o->kmc_time_step; }
+void kmos_oracle_set_kmc_time(oracle_t *o, double t) { o->kmc_time = t; } /* base.set_kmc_time */
 int64_t kmos_oracle_kmc_step(const oracle_t *o) { return o->kmc_step; }
 void kmos_oracle_get_lattice(const oracle_t *o, int32_t *out) { memcpy(out, o->lattice, (size_t)o->volume * 4); }
 void kmos_oracle_get_procstat(const oracle_t *o, int64_t *out) { memcpy(out, o->procstat, (size_t)o->n_proc * 8); }

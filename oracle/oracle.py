@@ -157,6 +157,13 @@ class Oracle(object):
         return self.L.kmos_oracle_kmc_time(self.h)
 
     @property
+    def kmc_time_step(self):
+        return self.L.kmos_oracle_kmc_time_step(self.h)
+
+    def set_kmc_time(self, t):
+        self.L.kmos_oracle_set_kmc_time(self.h, float(t))
+
+    @property
     def kmc_step(self):
         return self.L.kmos_oracle_kmc_step(self.h)
 

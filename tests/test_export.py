@@ -27,3 +27,11 @@ def test_export_tables_next_to_fortran(tmp_path):
     h = ctypes.c_void_p()
     assert capi.lib().kmos_b200_model_create(on_disk, on_disk.size, ctypes.byref(h)) == 0
     capi.lib().kmos_b200_model_destroy(h)
+    # ... and the exporter emitted the model's CUDA proclist next to the Fortran (north_star)
+    cu = d / "proclist_model.cu" if (d / "proclist_model.cu").exists() else info["proclist_cu"]
+    text = open(cu).read()
+    assert "KB_GEN_MODULE(KbModel, kb_info)" in text and "static constexpr int P = 36" in text
+    assert "static constexpr int LPR = 16" in text          # RuO2: 16 lanes per replica, two replicas per warp
+    assert text.count("// process ") == 36 and "replace_species(site + (0,0,0) type" in text
+    # lattice geometry for the front-end
+    assert ir["unit_cell_size"][0][0] == 10.0 and len(ir["site_positions"]) == 2
