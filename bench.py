@@ -522,6 +522,107 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_config(args, key, rank, world, local_rank):
+    """One of the other BASELINE configurations (A, B, D, E) as its own weak-scaling job: the configuration's
+    replica count PER GPU, replicas sharded over the ranks by global id, one NCCL tally all-reduce per step
+    (`--config E --gpus 8` is BASELINE.json configs[4]).  Same JSON contract, without the CPU arm."""
+    import torch
+    from kmos_b200 import engine, otf as otf_mod, parallel, tables, workloads
+    _k, label, name, size, R, inner = [c for c in CONFIGS if c[0] == key][0]
+    inner = args.inner if args.inner != 5000 else inner
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.Stream()
+    ir = tables.load_ir(os.path.join(REPO, "tests", "golden", "models", name + ".json"))
+    model = engine.Model(ir=ir)
+    P = model.n_proc
+    rates = workloads.rates_for(name.split("_")[0], ir, R)
+    lut = None
+    if ir["backend"] == "otf":
+        lut = np.tile(otf_mod.build_lut(ir, model.info, rates[0]), (R, 1))
+    gid = np.arange(rank * R, (rank + 1) * R)
+    seeds = gid.astype(np.uint64) * np.uint64(2654435761) + np.uint64(17)
+    batch = engine.Batch(model, R, size, device=local_rank, seeds=seeds, replica_ids=gid.astype(np.uint32),
+                         rates=rates, lut=lut)
+    batch.set_stream(stream.cuda_stream)
+    n_groups = 8
+    groups = (np.arange(R) * n_groups // R).astype(np.int32)
+    words = batch.tally_words()
+    tally = torch.zeros((n_groups, words), dtype=torch.float64, device="cuda")
+    count_cols = parallel.count_columns(P, model.n_species * model.spuck)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        with torch.cuda.stream(stream):
+            batch.do_steps(inner)
+            batch.reduce_tallies(groups, n_groups, dev_ptr=tally.data_ptr(), want_host=False)
+            parallel.all_reduce_tallies(tally, count_cols=count_cols)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+    t1.record(stream)
+    barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ok = bool(np.all(batch.status == 0))
+    steps_done = int(batch.kmc_step.min())
+    tl = batch.split_tally(tally.cpu().numpy())
+    checks = {"all_replicas_ok": ok, "kmc_steps_per_replica_total": steps_done,
+              "tally_n_replicas": float(tl["n_replicas"].sum()), "tally_kmc_steps": float(tl["kmc_steps"].sum())}
+    assert checks["tally_n_replicas"] == world * R, checks
+    if ok:
+        assert checks["tally_kmc_steps"] == float(world) * R * steps_done, checks
+    kinfo = batch.kernel_info()
+    ns = float(batch.nr_of_sites.sum(axis=1).mean())
+    batch.close()
+    if rank == 0:
+        total = float(R) * inner * args.steps * world
+        line = {"metric": "aggregate kMC steps/s over replicas, %s" % label, "value": total / (ms * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": label, "baseline_config": key, "model": name, "lattice": size,
+                           "replicas_per_gpu": R, "kmc_steps_per_replica_per_step": inner,
+                           "parallelism": "replica-sharded, %d GPU(s), tally all-reduce per step (int64 counts + f64 sums)" % world,
+                           "l2": "no flush: the state a step touches exceeds the 126 MB L2" if key in "DE" else
+                                 "state per GPU: %d replicas" % R},
+                "kernel": kinfo, "checks": checks, "clocks": clocks, "gpu_launches": 3 * args.steps}
+        if key == "E":
+            b_step = 8.0 * ns
+            peaks = {}
+            try:
+                with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+                    peaks = json.load(f)
+            except (OSError, ValueError):
+                pass
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            ach = b_step * R * inner * args.steps / (ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                                "traffic": _ncu_dram_bytes("E")[0], "algorithmic_bytes_per_kmc_step": b_step,
+                                "note": "per GPU; every live rates_matrix entry is re-added every step"}
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -531,6 +632,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=800000, help="kMC steps per replica of the CPU sample")
     ap.add_argument("--no-configs", action="store_true", help="skip the other four BASELINE configurations")
+    ap.add_argument("--config", default="C", choices=["A", "B", "C", "D", "E"],
+                    help="BASELINE configuration to run as the job (default C, the headline)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -541,6 +644,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config != "C":
+        run_config(args, args.config, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -115,17 +115,18 @@ int kmos_b200_init_state(kmos_b200_batch *b, int32_t layer);
  * species[V] (replica >= 0) or species[R][V] (replica = -1), site-number order. */
 int kmos_b200_set_configuration(kmos_b200_batch *b, int32_t replica, const int32_t *species, int32_t layer);
 
-/* proclist.do_kmc_steps(n) (proclist_generic_subroutines.mpy:1-44) on every replica.  Asynchronous on the
- * batch's stream; getters synchronise. */
 /* base.reload_system (base.mpy:365-510) for one replica: the arrays of the reference's <system_name>.reload file
  * (written by base.save_system, :517-578) restored verbatim -- lattice[V], avail_sites[P][V][2] in the layout
  * of kmos_b200_get_avail_sites (order preserved, no touch-up), nr_of_sites[P], procstat[P], kmc_time, kmc_step
  * -- plus integ_rates[P] (NULL = zeros; the reference's file forgets them).  The Philox stream continues at
- * kmc_step.  Not available for otf (rates_matrix is part of its state). */
+ * kmc_step.  otf: the file carries no rates_matrix (nor does the reference's, base_otf.f90:602-663); the rows are
+ * rebuilt from the restored lattice and the current gr_<proc> table (proclist.recalculate_rates_matrix). */
 int kmos_b200_reload_replica(kmos_b200_batch *b, int32_t replica, const int32_t *species, const int32_t *avail_sites,
                              const int32_t *nr_of_sites, const int64_t *procstat, const double *integ_rates,
                              double kmc_time, int64_t kmc_step);
 
+/* proclist.do_kmc_steps(n) (proclist_generic_subroutines.mpy:1-44) on every replica.  Asynchronous on the
+ * batch's stream; getters synchronise. */
 int kmos_b200_do_kmc_steps(kmos_b200_batch *b, int64_t n);
 int kmos_b200_synchronize(kmos_b200_batch *b);
 /* proclist.get_next_kmc_step(proc, site) (proclist_generic_subroutines.mpy:85-110) for every replica: the next

@@ -1269,7 +1269,6 @@ extern "C" int kmos_b200_reload_replica(kmos_b200_batch* b, int32_t replica, con
     if (!species || !avail || !nr_of_sites || !procstat || replica < 0 || replica >= b->R)
         return set_err(KMOS_B200_ERR_ARG, "reload_replica: bad argument");
     const KbModelView& m = b->model->h;
-    if (m.backend == KB_BACKEND_OTF) return set_err(KMOS_B200_ERR_UNSUPPORTED, "reload_replica: otf keeps rates_matrix, not supported");
     const int P = m.n_proc, C = b->g.ncells, V = b->g.volume, sp = m.spuck;
     std::vector<uint8_t> lat(b->lat_stride, KB_NULL_SPECIES);
     for (int i = 0; i < V; ++i) {
@@ -1309,6 +1308,14 @@ extern "C" int kmos_b200_reload_replica(kmos_b200_batch* b, int32_t replica, con
     sc.kmc_time = kmc_time; sc.kmc_step = kmc_step; sc.kmc_time_step = 0.0; sc.status = KB_OK;
     for (int i = 0; i < 5; ++i) sc.err[i] = 0;
     CU(kb_h2d(b, b->sc + replica, &sc, sizeof sc));
+    b->initialised = true;
+    if (m.backend == KB_BACKEND_OTF) {
+        // The reference's restart file carries no rates_matrix (base_otf.f90:602-663): after reload_system the
+        // front-end's set_rate_constants ends with proclist.recalculate_rates_matrix.  Same here: every
+        // registered rate is a function of the restored lattice (gr_<proc> table), the rows are re-added.
+        CU(cudaMemsetAsync(b->rates_matrix + (size_t)replica * P * (C + 1), 0, (size_t)P * (C + 1) * 8, b->stream));
+        return launch_generic(b, KB_MODE_RECALC, 0, 0, replica);
+    }
     return launch_generic(b, KB_MODE_ACCUM, 0, 0, replica);
 }
 

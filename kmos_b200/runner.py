@@ -20,6 +20,8 @@ import numpy as np
 from .model import KMC_Model
 
 
+# ModelParameter and its four subclasses are an API mirror of kmos/run/__init__.py:1896-1985 (same constructor
+# arguments, same __repr__, same grids) so that existing ModelRunner subclasses keep working unchanged.
 class ModelParameter(object):
     """A variable to scan: ``min``, ``max``, ``steps`` (kmos/run/__init__.py:1896-1925)."""
 
@@ -73,12 +75,47 @@ class LinearParameter(ModelParameter):
         super(LinearParameter, self).__init__(*a, **k)
 
 
-class ModelRunner(object):
-    """Subclass and declare ModelParameter attributes, or pass ``parameters={name: ModelParameter}``."""
+def _run_points(model_path, size, seeds, points, first_point, device, init_steps, sample_steps, samples,
+                random_seed, model_factory=None):
+    """The rows of `points` (grid points first_point, first_point+1, ... of the whole scan), `seeds` replicas
+    each, as one batch on one GPU.  Philox keys follow the *global* replica index, so a scan gives the same
+    rows however its points are dealt to GPUs.  -> (header, rows[len(points)*seeds][fields], parameter dump)"""
+    per_rep = [pt for pt in points for _ in range(seeds)]
+    gid = first_point * seeds + np.arange(len(per_rep))
+    keys = (np.uint64(random_seed) + gid.astype(np.uint64))
+    factory = model_factory or KMC_Model
+    with factory(model_path, size=size, n_replicas=len(per_rep), parameters=per_rep, device=device,
+                 seeds=keys) as model:
+        model.do_steps(int(init_steps))
+        model.get_atoms_all()
+        rows = model.get_std_sampled_data_all(samples, int(sample_steps), tof_method="integ")
+        header = model.get_std_header()
+        params_dump = "".join("# %s = %s\n" % (k, v) for k, v in sorted(model.get_parameters(0).items()))
+    return header, np.asarray(rows), params_dump
 
-    def __init__(self, model, size=20, seeds=1, parameters=None, device=0, name=None):
+
+def _spawn_worker(conn, args):
+    try:
+        conn.send(("ok", _run_points(*args)))
+    except Exception as e:  # the parent re-raises
+        import traceback
+        conn.send(("error", "%s\n%s" % (e, traceback.format_exc())))
+    finally:
+        conn.close()
+
+
+class ModelRunner(object):
+    """Subclass and declare ModelParameter attributes, or pass ``parameters={name: ModelParameter}``.
+
+    API mirror of kmos.run.ModelRunner (kmos/run/__init__.py:2005-2366): the reference's ``run(cores=N)`` deals
+    grid points to a pool of N processes that append to one ``.dat`` file under a lock file; ``run(gpus=N)``
+    deals contiguous blocks of grid points (kmos_b200.parallel.shard_bounds) to N GPUs of the box -- one
+    process per GPU, no traffic while stepping -- gathers the rows on rank 0 and writes the same file."""
+
+    def __init__(self, model, size=20, seeds=1, parameters=None, device=0, name=None, model_factory=None):
         self.model_path, self.size, self.seeds, self.device = model, size, int(seeds), device
         self.runner_name = name or type(self).__name__
+        self.model_factory = model_factory
         self.parameters = OrderedDict()
         for klass in reversed(type(self).__mro__):
             for key, item in vars(klass).items():
@@ -91,18 +128,62 @@ class ModelRunner(object):
         grids = [p.get_grid() for p in self.parameters.values()]
         return [dict(zip(self.parameters.keys(), (float(v) for v in pt))) for pt in itertools.product(*grids)]
 
-    def run(self, init_steps=1e5, sample_steps=1e5, samples=1, random_seed=1, outfile=None, per_replica=False):
-        """Returns (header, rows).  One row per grid point (mean over its seeds) unless ``per_replica``."""
+    def _gather(self, points, gpus, args):
+        """-> (header, rows of every grid point in grid order, parameter dump), or None on ranks > 0."""
+        from . import parallel
+        try:
+            import torch.distributed as dist
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except ImportError:
+            distributed = False
+        if distributed:  # launched by torch.distributed.run: this process is one rank with its own GPU
+            rank, world = dist.get_rank(), dist.get_world_size()
+            lo, hi = parallel.shard_bounds(len(points), rank, world)
+            device = int(os.environ.get("LOCAL_RANK", rank))
+            mine = _run_points(self.model_path, self.size, self.seeds, points[lo:hi], lo, device, *args,
+                               model_factory=self.model_factory) if hi > lo else None
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(mine, parts, dst=0)
+            if rank != 0:
+                return None
+        elif gpus and gpus > 1:  # one worker process per GPU of this box
+            import multiprocessing as mp
+            ctx = mp.get_context("spawn")
+            jobs = []
+            for rank in range(gpus):
+                lo, hi = parallel.shard_bounds(len(points), rank, gpus)
+                if hi == lo:
+                    continue
+                parent, child = ctx.Pipe()
+                wargs = (self.model_path, self.size, self.seeds, points[lo:hi], lo, rank) + tuple(args) + \
+                    (self.model_factory,)
+                proc = ctx.Process(target=_spawn_worker, args=(child, wargs))
+                proc.start()
+                jobs.append((proc, parent))
+            parts = []
+            for proc, parent in jobs:
+                status, payload = parent.recv()
+                proc.join()
+                if status != "ok":
+                    raise RuntimeError("ModelRunner worker failed: %s" % payload)
+                parts.append(payload)
+        else:
+            parts = [_run_points(self.model_path, self.size, self.seeds, points, 0, self.device, *args,
+                                 model_factory=self.model_factory)]
+        parts = [p for p in parts if p is not None]
+        return parts[0][0], np.vstack([p[1] for p in parts]), parts[0][2]
+
+    def run(self, init_steps=1e5, sample_steps=1e5, samples=1, random_seed=1, outfile=None, per_replica=False,
+            gpus=None):
+        """Returns (header, rows).  One row per grid point (mean over its seeds) unless ``per_replica``.
+        gpus: number of GPUs of this box to deal the grid points to (default: one, ``device``); under
+        torch.distributed.run the ranks of the job are used instead and only rank 0 returns rows."""
         points = self.grid_points()
-        per_rep = [pt for pt in points for _ in range(self.seeds)]
         outfile = outfile or os.path.abspath("%s.dat" % self.runner_name)
-        with KMC_Model(self.model_path, size=self.size, n_replicas=len(per_rep), parameters=per_rep,
-                       device=self.device, random_seed=random_seed) as model:
-            model.do_steps(int(init_steps))
-            model.get_atoms_all()
-            rows = model.get_std_sampled_data_all(samples, int(sample_steps), tof_method="integ")
-            header = model.get_std_header()
-            params_dump = "".join("# %s = %s\n" % (k, v) for k, v in sorted(model.get_parameters(0).items()))
+        got = self._gather(points, gpus, (init_steps, sample_steps, samples, random_seed))
+        if got is None:
+            return None, None
+        header, rows, params_dump = got
         if not per_replica:
             rows = rows.reshape(len(points), self.seeds, -1).mean(axis=1)
         new = not os.path.exists(outfile)

@@ -1,0 +1,33 @@
+"""A stand-in for kmos_b200.model.KMC_Model with the methods ModelRunner uses: rows are a pure function of the
+parameter point and the Philox key, so sharded and unsharded scans can be compared on a machine without a GPU."""
+import numpy as np
+
+
+class FakeModel(object):
+    def __init__(self, model, size=20, n_replicas=1, parameters=None, device=0, seeds=None):
+        self.params, self.seeds, self.device = parameters, np.asarray(seeds, dtype=np.uint64), device
+        self.steps = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def do_steps(self, n):
+        self.steps += int(n)
+
+    def get_atoms_all(self):
+        return None
+
+    def get_std_sampled_data_all(self, samples, sample_steps, tof_method="integ"):
+        rows = []
+        for p, s in zip(self.params, self.seeds):
+            rows.append([p["T"], p["p_COgas"], float(s) * 1e-3, float(self.steps + sample_steps)])
+        return np.asarray(rows)
+
+    def get_std_header(self):
+        return "#T p_COgas tof kmc_steps\n"
+
+    def get_parameters(self, replica=0):
+        return dict(self.params[replica])
