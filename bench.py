@@ -245,6 +245,24 @@ def measure_configs(counters, headline_entry, device, smem_peak, hbm_peak):
         else:
             cnt, P = counters[key]
             b_step = algorithmic_bytes_per_step(P, cnt)
+        fast = None
+        if key == "E":
+            # the production selection on the same batch (kb_otf_fast.cuh: block sums, not bit-exact)
+            from kmos_b200 import capi
+            b.select_kernel(capi.KERNEL_OTF_FAST)
+            nf = 2000
+            b.do_steps(nf // 4)
+            b.synchronize()
+            ft = []
+            for _ in range(2):
+                b.timer_start()
+                b.do_steps(nf)
+                ft.append(b.timer_stop())
+            fast = {"config": "E-fast", "workload": label + ", production selection over block sums (kb_otf_fast.cuh; "
+                    "same distribution and prefix order, not bit-exact)", "model": name, "lattice": size,
+                    "replicas": R, "kmc_steps_per_launch": nf, "kernel": "otf_fast",
+                    "value": R * nf / (float(np.mean(ft)) * 1e-3), "unit": UNIT, "ms_per_launch": float(np.mean(ft)),
+                    "all_replicas_ok": bool((b.status == 0).all())}
         b.close()
         m.close()
         launch_bytes = b_step * R * n
@@ -259,6 +277,8 @@ def measure_configs(counters, headline_entry, device, smem_peak, hbm_peak):
             "roofline": {"bound": "smem" if in_smem else "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_kmc_step": b_step}})
+        if fast is not None:
+            out.append(fast)
     return out
 
 

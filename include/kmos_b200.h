@@ -52,7 +52,12 @@ enum {
     KMOS_B200_KERNEL_GENERIC = 1, /* thread-per-replica byte-code engine, state in HBM (all backends) */
     KMOS_B200_KERNEL_SMEM = 2,    /* warp-per-replica, state in shared memory (local_smart that fits) */
     KMOS_B200_KERNEL_WARP_HBM = 3, /* warp-per-replica, state in HBM/L2 (lat_int: nli_* decision trees per lane) */
-    KMOS_B200_KERNEL_GENERATED = 4 /* exporter-generated per-model CUDA (proclist_<model>.cu), local_smart */
+    KMOS_B200_KERNEL_GENERATED = 4, /* exporter-generated per-model CUDA (proclist_<model>.cu), local_smart */
+    KMOS_B200_KERNEL_OTF_FAST = 5  /* otf production mode: sub-linear event selection over block sums of
+                                    * rates_matrix (the O(log N) replacement the reference announces,
+                                    * doc/source/topic_guides/otf_backend.rst:198-202).  Same distribution, same
+                                    * prefix order, NOT bit-exact (floating-point association); never chosen by
+                                    * KMOS_B200_KERNEL_AUTO */
 };
 
 const char *kmos_b200_last_error(void);

@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 OK = 0
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SMEM, KERNEL_WARP_HBM, KERNEL_GENERATED = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SMEM, KERNEL_WARP_HBM, KERNEL_GENERATED, KERNEL_OTF_FAST = 0, 1, 2, 3, 4, 5
 BACKEND_LOCAL_SMART, BACKEND_LAT_INT, BACKEND_OTF = 0, 1, 2
 REPLICA_OK, REPLICA_DEADLOCK, REPLICA_SPECIES_MISMATCH, REPLICA_CAPACITY, REPLICA_BAD_MODEL = range(5)
 
@@ -27,7 +27,7 @@ class KmosB200Error(RuntimeError):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_otf.cuh", "kb_gen.cuh",
+    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_otf.cuh", "kb_otf_fast.cuh", "kb_gen.cuh",
                                             "kb_interp.h", "kb_common.h")] + \
         [os.path.join(os.path.dirname(HERE), "include", "kmos_b200.h")]
 

@@ -91,6 +91,8 @@ struct KbReplica {
     int64_t* procstat;  // [P]
     double* rates_matrix;  // otf: [P][ncells+1]; column ncells = row total (base_otf.f90:152-162)
     double* accum_proc;    // otf: [ncells]
+    double* blk = nullptr; // otf production kernel (kb_otf_fast.cuh): [P][blk_n] block sums of rates_matrix rows
+    int blk_n = 0;         //   over 256 positions, maintained by add_proc / del_proc / update_rates_matrix
     const double* lut;     // otf: [lut_total]
     double kmc_time, kmc_time_step;
     int64_t kmc_step;

@@ -53,6 +53,11 @@ struct KbInterp {
             r.p1[row + nq - 1] = 0;
             if (m.backend == KB_BACKEND_OTF) {
                 double* rm = r.rates_matrix + (size_t)(proc - 1) * (g.ncells + 1);
+                if (r.blk) {  // the moved rate changes block, the freed one leaves
+                    double* bl = r.blk + (size_t)(proc - 1) * r.blk_n;
+                    bl[(pos - 1) >> 8] += rm[nq - 1] - rm[pos - 1];
+                    bl[(nq - 1) >> 8] -= rm[nq - 1];
+                }
                 rm[g.ncells] = KB_SUB(rm[g.ncells], rm[pos - 1]);
                 rm[pos - 1] = rm[nq - 1];
                 rm[nq - 1] = 0.0;
@@ -62,6 +67,7 @@ struct KbInterp {
             r.p1[row + pos - 1] = 0;
             if (m.backend == KB_BACKEND_OTF) {
                 double* rm = r.rates_matrix + (size_t)(proc - 1) * (g.ncells + 1);
+                if (r.blk) r.blk[(size_t)(proc - 1) * r.blk_n + ((pos - 1) >> 8)] -= rm[pos - 1];
                 rm[g.ncells] = KB_SUB(rm[g.ncells], rm[pos - 1]);
                 rm[pos - 1] = 0.0;
             }
@@ -81,6 +87,7 @@ struct KbInterp {
         r.p2[row + cell] = (idx_t)nq;
         if (m.backend == KB_BACKEND_OTF) {
             double* rm = r.rates_matrix + (size_t)(proc - 1) * (g.ncells + 1);
+            if (r.blk) r.blk[(size_t)(proc - 1) * r.blk_n + ((nq - 1) >> 8)] += rate;
             rm[g.ncells] = KB_ADD(rm[g.ncells], rate);
             rm[nq - 1] = rate;
         }
@@ -89,6 +96,7 @@ struct KbInterp {
     KB_HD void update_rates_matrix(int proc, int cell, double rate) {
         double* rm = r.rates_matrix + (size_t)(proc - 1) * (g.ncells + 1);
         int pos = (int)r.p2[(size_t)(proc - 1) * g.ncells + cell];
+        if (r.blk) r.blk[(size_t)(proc - 1) * r.blk_n + ((pos - 1) >> 8)] += rate - rm[pos - 1];
         rm[g.ncells] = KB_SUB(KB_ADD(rm[g.ncells], rate), rm[pos - 1]);
         rm[pos - 1] = rate;
     }

@@ -25,6 +25,7 @@
 #include "kb_latint.cuh"
 #include "kb_otf.cuh"
 #include "kb_gen.cuh"
+#include "kb_otf_fast.cuh"
 
 #include <dlfcn.h>
 
@@ -703,10 +704,16 @@ extern "C" int kmos_b200_select_kernel(kmos_b200_batch* b, int32_t kind) {
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "shared-memory kernel unavailable: " + b->smem_reason);
     if (kind == KMOS_B200_KERNEL_WARP_HBM && !b->li_ok && !b->otf_ok)
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "warp-per-replica HBM kernel unavailable for this model/lattice");
+    if (kind == KMOS_B200_KERNEL_OTF_FAST) {
+        if (!b->otf_ok) return set_err(KMOS_B200_ERR_UNSUPPORTED, "the otf production kernel needs an otf model (up to 64 processes)");
+        const long long nblk = ((long long)b->g.ncells + KB_OTFF_BLOCK - 1) >> KB_OTFF_SHIFT;
+        if ((long long)b->model->h.n_proc * nblk > (long long)b->g.ncells)
+            return set_err(KMOS_B200_ERR_UNSUPPORTED, "otf production kernel: lattice too small for the block sums (P * ceil(ncells/256) > ncells)");
+    }
     if (kind == KMOS_B200_KERNEL_GENERATED && !b->gen_ok)
         return set_err(KMOS_B200_ERR_UNSUPPORTED, "no generated proclist attached (kmos_b200_batch_attach_proclist)");
     if (kind != KMOS_B200_KERNEL_SMEM && kind != KMOS_B200_KERNEL_GENERIC && kind != KMOS_B200_KERNEL_WARP_HBM &&
-        kind != KMOS_B200_KERNEL_GENERATED)
+        kind != KMOS_B200_KERNEL_GENERATED && kind != KMOS_B200_KERNEL_OTF_FAST)
         return set_err(KMOS_B200_ERR_ARG, "bad kernel kind");
     b->kernel = kind;
     return KMOS_B200_OK;
@@ -727,6 +734,8 @@ extern "C" int kmos_b200_kernel_info(kmos_b200_batch* b, int64_t info[12]) {
         info[7] = (b->R + b->gp.replicas_per_cta - 1) / b->gp.replicas_per_cta;
         if (info[7] > (int64_t)b->gp.sm_count * b->gp.ctas_per_sm) info[7] = (int64_t)b->gp.sm_count * b->gp.ctas_per_sm;
         info[8] = 1; info[9] = b->gp.regs; info[10] = 0; info[11] = b->gp.img_bytes;
+    } else if (b->kernel == KMOS_B200_KERNEL_OTF_FAST) {
+        info[1] = KB_OTFF_WARPS; info[4] = b->sm_count; info[7] = (b->R + KB_OTFF_WARPS - 1) / KB_OTFF_WARPS; info[8] = 1;
     } else if (b->kernel == KMOS_B200_KERNEL_WARP_HBM && b->otf_ok) {
         info[1] = KB_OTF_WARPS; info[2] = KB_OTF_SMEM; info[4] = b->sm_count;
         info[7] = (b->R + KB_OTF_WARPS - 1) / KB_OTF_WARPS; info[8] = 1;
@@ -1049,7 +1058,7 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
     if (n == 0) return KMOS_B200_OK;
     if (b->kernel == KMOS_B200_KERNEL_GENERIC) return launch_generic(b, KB_MODE_STEPS, n, 0, -1);
     CU(cudaSetDevice(b->device));
-    if (b->kernel == KMOS_B200_KERNEL_WARP_HBM && b->otf_ok) {
+    if ((b->kernel == KMOS_B200_KERNEL_WARP_HBM || b->kernel == KMOS_B200_KERNEL_OTF_FAST) && b->otf_ok) {
         int rc0 = ensure_canonical(b);
         if (rc0) return rc0;
         KbOtfParams op;
@@ -1058,6 +1067,13 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
         op.lattice = b->lattice; op.p1 = b->p1; op.p2 = b->p2; op.nsites = b->nsites; op.rates = b->rates;
         op.integ = b->integ; op.accum = b->accum; op.procstat = b->procstat; op.sc = b->sc;
         op.rates_matrix = b->rates_matrix; op.accum_proc = b->accum_proc; op.lut = b->lut; op.nsteps = n;
+        if (b->kernel == KMOS_B200_KERNEL_OTF_FAST) {
+            const int fblocks = (b->R + KB_OTFF_WARPS - 1) / KB_OTFF_WARPS;
+            if (b->idx32) kb_otf_fast_kernel<uint32_t><<<fblocks, 32 * KB_OTFF_WARPS, 0, b->stream>>>(op);
+            else kb_otf_fast_kernel<uint16_t><<<fblocks, 32 * KB_OTFF_WARPS, 0, b->stream>>>(op);
+            CU(cudaGetLastError());
+            return KMOS_B200_OK;
+        }
         const int threads = 32 * KB_OTF_WARPS, blocks = (b->R + KB_OTF_WARPS - 1) / KB_OTF_WARPS;
         if (b->idx32) {
             CU(cudaFuncSetAttribute(kb_otf_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_OTF_SMEM));

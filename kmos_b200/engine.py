@@ -129,7 +129,8 @@ class Batch(object):
                 "image_bytes_per_replica")
         d = dict(zip(keys, (int(x) for x in info)))
         d["kernel_name"] = {capi.KERNEL_GENERIC: "generic", capi.KERNEL_SMEM: "smem",
-                            capi.KERNEL_WARP_HBM: "warp_hbm", capi.KERNEL_GENERATED: "generated"}[d["kernel"]]
+                            capi.KERNEL_WARP_HBM: "warp_hbm", capi.KERNEL_GENERATED: "generated",
+                            capi.KERNEL_OTF_FAST: "otf_fast"}[d["kernel"]]
         return d
 
     def set_seeds(self, seeds, replica_ids=None):
