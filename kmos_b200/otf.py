@@ -34,7 +34,9 @@ def _powi(x, m):
 
 def _fpow(a, b):
     if isinstance(b, (int, np.integer)) and not isinstance(b, bool):
-        return _powi(float(a), int(b))
+        return _powi(a if isinstance(a, np.ndarray) else float(a), int(b))
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        return np.power(a, b)
     return math.pow(a, b)
 
 
@@ -47,8 +49,9 @@ class _PowToCall(ast.NodeTransformer):
         return node
 
 
-def fortran_expr_to_callable(expr, proc_ids, userpar_ids, chempot_ids, constants):
-    """Translate a generated `rate_<proc>` right-hand side into f(rates, userpar, chempots, nr_vars)."""
+def fortran_expr_to_callable(expr, proc_ids, userpar_ids, chempot_ids, constants, functions=None):
+    """Translate a generated `rate_<proc>` right-hand side into f(rates, userpar, chempots, nr_vars).
+    functions: replacements for the elementary functions (numpy's, for array arguments)."""
     py = expr
     py = re.sub(r"\brates\s*\(\s*(\w+)\s*\)", lambda m: "rates[%d]" % (proc_ids[m.group(1).lower()] - 1), py)
     py = re.sub(r"\buserpar\s*\(\s*(\w+)\s*\)", lambda m: "userpar[%d]" % userpar_ids[m.group(1)], py)
@@ -62,11 +65,14 @@ def fortran_expr_to_callable(expr, proc_ids, userpar_ids, chempot_ids, constants
           "sin": math.sin, "cos": math.cos, "abs": abs, "min": min, "max": max}
     for k, v in constants.items():
         ns[k] = float(v)
+    if functions:
+        ns.update(functions)
 
     def f(rates, userpar, chempots, nr_vars):
         env = dict(ns)
         env.update(rates=rates, userpar=userpar, chempots=chempots, nr_vars=nr_vars)
-        return float(eval(code, env))
+        out = eval(code, env)
+        return out if functions else float(out)
     return f
 
 
@@ -85,6 +91,38 @@ def user_parameters(ir, overrides=None):
         chempots.append(standin_mu(species, evaluate_rate_expression(str(params["T"]["value"]), params),
                                    evaluate_rate_expression(str(params["p_" + species]["value"]), params)))
     return userpar, chempots
+
+
+def build_lut_batch(ir, info, rates, overrides_list=None):
+    """lut[R][lut_total] for R replicas at once: every table entry is evaluated once over all replicas (numpy
+    arrays for rates[R][P] and the user parameters) instead of once per replica and entry."""
+    rates = np.asarray(rates, dtype=float)
+    R = rates.shape[0]
+    lut = np.zeros((R, max(info["lut_total"], 1)))
+    proc_ids = {p.lower(): i + 1 for i, p in enumerate(ir["procs"])}
+    userpar_ids = {n: i for i, n in enumerate(ir.get("userpar", []))}
+    chempot_ids = {n: i for i, n in enumerate(ir.get("chempots", []))}
+    ups = [user_parameters(ir, (overrides_list[r] if overrides_list else None)) for r in
+           (range(R) if overrides_list else range(1))]
+    userpar = [np.array([u[0][k] for u in ups]) for k in range(len(ir.get("userpar", [])))]
+    chempots = [np.array([u[1][k] for u in ups]) for k in range(len(ir.get("chempots", [])))]
+    cols = [rates[:, q] for q in range(rates.shape[1])]
+    by_lower = {k.lower(): v for k, v in ir["rate_expr"].items()}
+    np_ns = {"exp": np.exp, "sqrt": np.sqrt, "log": np.log, "sin": np.sin, "cos": np.cos, "abs": np.abs,
+             "min": np.minimum, "max": np.maximum}
+    for name, g in info["gr"].items():
+        expr = by_lower[name[len("gr_"):].lower()]
+        f = fortran_expr_to_callable(expr, proc_ids, userpar_ids, chempot_ids, ir.get("pars_constants", {}),
+                                     functions=np_ns)
+        radix = g["radix"]
+        for combo in itertools.product(*[range(r) for r in reversed(radix)]):
+            nv = list(reversed(combo))
+            idx, stride = 0, 1
+            for k, r in enumerate(radix):
+                idx += nv[k] * stride
+                stride *= r
+            lut[:, g["lut_offset"] + idx] = f(cols, userpar, chempots, nv)
+    return lut
 
 
 def build_lut(ir, info, rates, overrides=None):

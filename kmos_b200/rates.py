@@ -58,12 +58,17 @@ class MuStandinWarning(UserWarning):
 def standin_mu(name, T, p):
     """Chemical potential stand-in in eV: linear-in-T entropy term + k_B T ln p (T in K, p in bar).
     NOT the JANAF value the reference uses; a gas without an entry gives 0 with a warning, as the reference
-    does for a species without a table."""
+    does for a species without a table.  Accepts numpy arrays for T and p (model_rates_grid)."""
     key = name if name in _MU_STANDIN else name + "gas"
     if key not in _MU_STANDIN:
         warnings.warn("No chemical-potential table for %s: setting it to zero" % name, MuStandinWarning)
         return 0.0
     a, b = _MU_STANDIN[key]
+    if hasattr(T, "shape") or hasattr(p, "shape"):
+        import numpy as np
+        T, p = np.asarray(T, dtype=float), np.asarray(p, dtype=float)
+        return a + b * (T - 298.15) * 0.5 + b * T * 0.5 * np.log(np.maximum(T, 1.0) / 298.15) \
+            + _KB_EV * T * np.log(p)
     T = float(T)
     return a + b * (T - 298.15) * 0.5 + b * T * 0.5 * math.log(max(T, 1.0) / 298.15) \
         + _KB_EV * T * math.log(float(p))
@@ -147,6 +152,79 @@ def evaluate_rate_expression(rate_expr, parameters=None, mu=None, masses=ATOMIC_
             replaced.append((i, token))
     expr = tokenize.untokenize(replaced)
     return float(eval(expr, {"__builtins__": {}, "math": math}))
+
+
+def evaluate_rate_expression_grid(rate_expr, parameters, grid, mu=None, masses=ATOMIC_MASSES):
+    """evaluate_rate_expression over a whole sweep at once: `grid` maps parameter names to numpy arrays (one
+    entry per sweep point, broadcastable); every other parameter keeps its scalar value.  One tokenisation and
+    one eval per expression instead of one per sweep point.  -> array of the grid's shape (float64).
+    Same substitutions as the scalar routine; transcendental functions are numpy's, which may differ from
+    libm's in the last bit."""
+    import numpy as np
+    pdict = {k: (v["value"] if isinstance(v, dict) else v) for k, v in (parameters or {}).items()}
+    shape = np.broadcast(*[np.asarray(v) for v in grid.values()]).shape if grid else ()
+    if not rate_expr:
+        return np.zeros(shape)
+    for old, new in RATE_ALIASES.items():
+        rate_expr = rate_expr.replace(old, new)
+    env = {"__builtins__": {}, "np": np}
+    for k, v in grid.items():
+        env["_g_" + k] = np.asarray(v, dtype=float)
+
+    def value_of(name):
+        return env["_g_" + name] if name in grid else float(evaluate_rate_expression(str(pdict[name]), parameters))
+
+    replaced = []
+    for i, token, _, _, _ in tokenize.generate_tokens(StringIO(rate_expr).readline):
+        if token in ["sqrt", "exp", "sin", "cos", "log"]:
+            replaced.append((i, "np." + token))
+        elif token == "pow":
+            replaced.append((i, "np.power"))
+        elif token == "pi":
+            replaced.append((i, str(UNITS["pi"])))
+        elif token in UNITS:
+            replaced.append((i, str(UNITS[token])))
+        elif token.startswith("m_"):
+            species_name = "_".join(token.split("_")[1:])
+            replaced.append((i, "%s" % sum(masses[s] for s in _string2symbols(species_name))))
+        elif token.startswith("mu_"):
+            species_name = "_".join(token.split("_")[1:])
+            f = resolve_mu(mu)
+            T, p = value_of("T"), value_of("p_%s" % species_name)
+            try:
+                val = f(species_name, T, p)
+            except TypeError:  # a provider without array support
+                val = np.vectorize(lambda t_, p_: f(species_name, float(t_), float(p_)))(T, p)
+            env["_mu_" + species_name] = val
+            replaced.append((i, "_mu_" + species_name))
+        elif token in grid:
+            replaced.append((i, "_g_" + token))
+        elif token in pdict:
+            s = str(pdict[token])
+            for unit in UNIT_KEYS:
+                s = s.replace(unit, "%s" % UNITS[unit])
+            replaced.append((i, s))
+        else:
+            replaced.append((i, token))
+    out = eval(tokenize.untokenize(replaced), env)
+    return np.broadcast_to(np.asarray(out, dtype=float), shape).copy()
+
+
+def model_rates_grid(ir, grid, overrides=None, **kw):
+    """rates[points][P]: model_rates for every point of a sweep in one pass per process (`grid`: parameter
+    name -> array over the sweep points)."""
+    import numpy as np
+    params = {k: dict(v) for k, v in ir["parameters"].items()}
+    for k, v in (overrides or {}).items():
+        params.setdefault(k, {})["value"] = v
+    by_name = {p["name"].lower(): p for p in ir["process_defs"]}
+    n = np.broadcast(*[np.asarray(v) for v in grid.values()]).shape
+    cols = []
+    for name in ir["procs"]:
+        pd = by_name[name.lower()]
+        cols.append(evaluate_rate_expression_grid(pd["rate_constant"], params, grid, **kw) if pd["enabled"]
+                    else np.zeros(n))
+    return np.stack([np.asarray(c, dtype=float).reshape(-1) for c in cols], axis=1)
 
 
 def model_rates(ir, overrides=None, **kw):

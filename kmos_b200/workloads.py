@@ -14,12 +14,10 @@ def ruo2_grid(ir, n_T=16, n_p=16, seeds=64, T_range=(450.0, 650.0), p_range=(1e-
     """rates[n_T*n_p*seeds][36], group_of[R] (grid point index), grid description."""
     Ts = np.linspace(T_range[0], T_range[1], n_T)
     ps = np.logspace(np.log10(p_range[0]), np.log10(p_range[1]), n_p)
-    points = []
-    for T in Ts:
-        for p in ps:
-            points.append(rates_mod.model_rates(ir, {"T": float(T), "p_COgas": float(p), "p_O2gas": float(p_O2)},
-                                                mu=rates_mod.standin_mu))
-    points = np.asarray(points)
+    # the whole T x p_CO grid in one vectorised pass per process (rates.model_rates_grid)
+    TT, PP = np.meshgrid(Ts, ps, indexing="ij")
+    points = rates_mod.model_rates_grid(ir, {"T": TT.reshape(-1), "p_COgas": PP.reshape(-1)},
+                                        overrides={"p_O2gas": float(p_O2)}, mu=rates_mod.standin_mu)
     rates = np.repeat(points, seeds, axis=0)
     group_of = np.repeat(np.arange(len(points), dtype=np.int32), seeds)
     return rates, group_of, {"T": Ts.tolist(), "p_COgas": ps.tolist(), "p_O2gas": p_O2, "seeds": seeds}

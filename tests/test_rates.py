@@ -87,3 +87,30 @@ def test_mu_tokens_use_a_provider_or_warn_about_the_standin():
         rates.evaluate_rate_expression("mu_COgas", params, mu=rates.standin_mu)
     with pytest.raises(KeyError):
         rates.evaluate_rate_expression("mu_O2gas", params, mu=rates.standin_mu)
+
+
+def test_vectorised_rate_preparation_matches_the_point_by_point_one():
+    """workloads.ruo2_grid / otf LUTs over a whole sweep in one pass per expression."""
+    import time
+
+    import numpy as np
+
+    from kmos_b200 import otf as otf_mod, tables, workloads
+    ir, _blob, _info = load_model("ruo2_local_smart")
+    Ts, ps = np.linspace(450.0, 650.0, 5), np.logspace(-2, 2, 4)
+    TT, PP = np.meshgrid(Ts, ps, indexing="ij")
+    grid = rates.model_rates_grid(ir, {"T": TT.reshape(-1), "p_COgas": PP.reshape(-1)},
+                                  overrides={"p_O2gas": 1.0}, mu=rates.standin_mu)
+    ref = np.asarray([rates.model_rates(ir, {"T": float(T), "p_COgas": float(p), "p_O2gas": 1.0}, mu=rates.standin_mu)
+                      for T in Ts for p in ps])
+    assert grid.shape == ref.shape == (20, 36)
+    np.testing.assert_allclose(grid, ref, rtol=1e-13, atol=0)
+    t0 = time.time()
+    r, group_of, _d = workloads.ruo2_grid(ir)
+    assert r.shape == (16384, 36) and group_of[-1] == 255 and time.time() - t0 < 5.0
+    # otf tables for many replicas at once
+    ir2, blob2, info2 = load_model("intzgb_otf")
+    rr = np.exp(np.random.RandomState(0).uniform(-1, 1, (7, len(ir2["procs"]))))
+    batch = otf_mod.build_lut_batch(ir2, info2, rr)
+    one = np.stack([otf_mod.build_lut(ir2, info2, rr[i]) for i in range(7)])
+    np.testing.assert_allclose(batch, one, rtol=1e-14, atol=0)
