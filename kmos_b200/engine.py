@@ -94,13 +94,6 @@ class Batch(object):
         from . import codegen, devtables
         path = proclist
         if proclist in ("auto", "build"):
-            if lpr is None and not os.environ.get("KMOS_B200_GEN_LPR"):
-                # few replicas per SM (a strong-scaling shard): a full warp per replica keeps more warps
-                # resident and has the shortest rounds; the generator's narrower groups pay when the
-                # replicas outnumber the warp slots
-                sm = self.kernel_info().get("sm_count", 0)
-                if sm and self.R <= 16 * sm:
-                    lpr = 32
             try:
                 path = codegen.find_built(self.model.ir, self.model.blob, lpr=lpr)
                 if path is None and (proclist == "build" or shutil.which(os.environ.get("NVCC", "nvcc"))):

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """One-off soak: every fixture x every kernel that accepts it, odd lattice sizes, long runs, all replicas compared
 with the oracle (lattice, procstat, nr_of_sites bit-exact; kmc_time 1e-12) at two checkpoints.  Not part of the
-test suite (minutes of oracle time); prints one line per case and a summary, writes gpurun_out/soak_r1.json."""
+test suite (minutes of oracle time); prints one line per case and a summary, writes gpurun_out/soak_r2.json.
+Round 2: the generated kernel at every lane-group width (gen8 / gen16 / gen32) is part of it."""
 import glob
 import json
 import os
@@ -15,11 +16,12 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 from conftest import load_model  # noqa: E402
 from util import make_inputs, oracle_checkpoints  # noqa: E402
-from kmos_b200 import capi, engine  # noqa: E402
+from kmos_b200 import capi, devtables, engine  # noqa: E402
 
-KERNELS = {"local_smart": ["smem", "warp_hbm", "generic"], "lat_int": ["warp_hbm", "generic"],
+KERNELS = {"local_smart": ["gen8", "gen16", "gen32", "smem", "warp_hbm", "generic"], "lat_int": ["warp_hbm", "generic"],
            "otf": ["warp_hbm", "generic"]}
-KIND = {"smem": capi.KERNEL_SMEM, "warp_hbm": capi.KERNEL_WARP_HBM, "generic": capi.KERNEL_GENERIC}
+KIND = {"smem": capi.KERNEL_SMEM, "warp_hbm": capi.KERNEL_WARP_HBM, "generic": capi.KERNEL_GENERIC,
+        "gen8": capi.KERNEL_GENERATED, "gen16": capi.KERNEL_GENERATED, "gen32": capi.KERNEL_GENERATED}
 
 
 def main():
@@ -43,8 +45,9 @@ def main():
         model = engine.Model(ir=ir, blob=blob, info=info)
         for k in KERNELS[backend]:
             try:
-                b = engine.Batch(model, R, size, seeds=seeds, rates=rates, lut=lut, kernel=KIND[k])
-            except capi.KmosB200Error as e:
+                kw = {"lpr": int(k[3:])} if k.startswith("gen") else {"proclist": None}
+                b = engine.Batch(model, R, size, seeds=seeds, rates=rates, lut=lut, kernel=KIND[k], **kw)
+            except (capi.KmosB200Error, devtables.Unsupported) as e:
                 out.append({"model": name, "kernel": k, "size": size, "skipped": str(e)[-80:]})
                 print(json.dumps(out[-1]), flush=True)
                 continue
@@ -61,7 +64,7 @@ def main():
                         "oracle_s": round(t_or, 1)})
             print(json.dumps(out[-1]), flush=True)
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(REPO, "gpurun_out", "soak_r1.json"), "w") as f:
+    with open(os.path.join(REPO, "gpurun_out", "soak_r2.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("cases %d, failed %d" % (len([o for o in out if "ok" in o]), bad))
     return 1 if bad else 0
