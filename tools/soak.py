@@ -45,7 +45,7 @@ def main():
         model = engine.Model(ir=ir, blob=blob, info=info)
         for k in KERNELS[backend]:
             try:
-                kw = {"lpr": int(k[3:])} if k.startswith("gen") else {"proclist": None}
+                kw = {"lpr": int(k[3:])} if k[3:].isdigit() else {"proclist": None}
                 b = engine.Batch(model, R, size, seeds=seeds, rates=rates, lut=lut, kernel=KIND[k], **kw)
             except (capi.KmosB200Error, devtables.Unsupported) as e:
                 out.append({"model": name, "kernel": k, "size": size, "skipped": str(e)[-80:]})
