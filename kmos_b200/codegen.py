@@ -43,7 +43,7 @@ MAX_COND = 4
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
 # threads per CTA the kernel is compiled for (register budget 65536 / threads): narrow groups run fewer warps
-MAX_THREADS = {32: 768, 16: 512, 8: 512}
+MAX_THREADS = {32: 768, 16: 640, 8: 512}
 
 
 def fnv1a(data):
@@ -200,7 +200,7 @@ def generate(ir, blob=None, name=None, lpr=None):
     lay = layout(an)
     rounds = lay["rounds"]
     lpr = an["lpr"]
-    max_threads = MAX_THREADS[lpr]
+    max_threads = int(os.environ.get("KMOS_B200_GEN_MAX_THREADS", MAX_THREADS[lpr]))  # experiments: register budget
     fx = ir.get("fixture")
     name = name or ir.get("model_name") or (fx.get("model") if isinstance(fx, dict) else fx) or "model"
     ident = "".join(ch if ch.isalnum() else "_" for ch in name)

@@ -217,21 +217,21 @@ struct KbGenCtx {
     // Both as one predicated sequence: the groups of a warp (and the lanes of a group) mix them freely.
     __device__ __forceinline__ void round(const int count, const uint32_t a, const KbGenOpB& b) {
         const bool valid = sl < count;
-        const uint32_t ca2 = kb_ldc16(nbrow + (a & 0xffu));
+        const uint32_t ca2 = kb_ldc16(nbrow + __byte_perm(a, 0u, 0x4440u));
         bool ok = valid;
 #pragma unroll
         for (int j = 0; j < M::BW; ++j) {
             const uint32_t w = b.c[j];  // unused probe slots are always true (see kb_gen_fill_tables)
-            const uint32_t cc2 = kb_ldc16(nbrow + (w & 0xffu));
-            const uint32_t sp = kb_lds8(lat + ((w >> 8) & 0xffu) + lat_index(cc2));
+            const uint32_t cc2 = kb_ldc16(nbrow + __byte_perm(w, 0u, 0x4440u));
+            const uint32_t sp = kb_lds8(lat + __byte_perm(w, 0u, 0x4441u) + lat_index(cc2));
             ok = ok && (kb_shr(w, 16u + sp) & 1u);
         }
-        const uint32_t q4 = (a >> 16) & 0xffu;  // 4 * process
+        const uint32_t q4 = __byte_perm(a, 0u, 0x4442u);  // byte 2: 4 * process (one PRMT)
         const uint32_t nsa = wns + q4;
         const uint32_t nsw = kb_lds32(nsa);
         const int nq = (int)(nsw & 0xffffu);
         int lo = (int)(nsw >> 16);
-        const uint32_t plane = wb + ((a >> 8) & 0xffu) * pl2;
+        const uint32_t plane = wb + __byte_perm(a, 0u, 0x4441u) * pl2;
         const uint32_t ea = plane + ca2;
         const uint32_t e = kb_lds16(ea);
         const uint32_t wina = win + 2u * q4;

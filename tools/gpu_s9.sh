@@ -1,0 +1,18 @@
+#!/bin/bash
+for T in 512 640 768; do for S in 20 14; do
+KMOS_B200_GEN_MAX_THREADS=$T python - <<PY
+import sys
+sys.path.insert(0, ".")
+from kmos_b200 import capi, engine, tables, workloads
+ir = tables.load_ir("tests/golden/models/ruo2_local_smart.json")
+m = engine.Model(ir=ir)
+R, n = 16384, 5000
+b = engine.Batch(m, R, [$S, $S], rates=workloads.rates_for("ruo2", ir, R), kernel=capi.KERNEL_GENERATED, lpr=16)
+info = b.kernel_info()
+b.do_steps(n); b.synchronize()
+best = None
+for _ in range(3):
+    b.timer_start(); b.do_steps(n); ms = b.timer_stop(); best = ms if best is None else min(best, ms)
+print("maxthreads $T size %d  replicas/CTA %d x %d CTAs/SM regs %d  %.3f ms  %.3e steps/s" % ($S, info["replicas_per_cta"], info["ctas_per_sm"], info["registers"], best, R * n / (best * 1e-3)))
+PY
+done; done
