@@ -179,16 +179,19 @@ def _counter_worker(args):
     o = oracle.Oracle(blob, size, seed=99, replica=0, rates=r)
     o.do_steps(n // 4)
     o.reset_counters()
+    t0 = time.perf_counter()
     o.do_steps(n)
+    dt = time.perf_counter() - t0
     c = o.counters
-    return {k: c[k] / float(n) for k in ("n_rs", "n_chk", "n_del", "n_gs", "n_add")}, len(ir["procs"])
+    # steps/s of the CPU port on ONE core: the `kmos benchmark` figure (README of the reference: 6.62e5 for config A)
+    return {k: c[k] / float(n) for k in ("n_rs", "n_chk", "n_del", "n_gs", "n_add")}, len(ir["procs"]), n / dt
 
 
 def config_counters():
     """Per-step event counters of configs A, B and D from a short oracle run each, in forked
     workers before CUDA is initialised.  -> {key: (counters, P)}"""
     import multiprocessing as mp
-    jobs = [(k, (name, size, 20000)) for k, _l, name, size, _R, _n in CONFIGS if k in "ABD"]
+    jobs = [(k, (name, size, 1000000 if k == "A" else 20000)) for k, _l, name, size, _R, _n in CONFIGS if k in "ABD"]
     with mp.get_context("fork").Pool(len(jobs)) as pool:
         res = pool.map(_counter_worker, [j[1] for j in jobs])
     return {k: r for (k, _), r in zip(jobs, res)}
@@ -243,7 +246,7 @@ def measure_configs(counters, headline_entry, device, smem_peak, hbm_peak):
             ns1 = b.nr_of_sites.sum(axis=1).mean()
             b_step = 8.0 * 0.5 * (ns0 + ns1)
         else:
-            cnt, P = counters[key]
+            cnt, P, _cpu1 = counters[key]
             b_step = algorithmic_bytes_per_step(P, cnt)
         fast = None
         if key == "E":
@@ -277,6 +280,9 @@ def measure_configs(counters, headline_entry, device, smem_peak, hbm_peak):
             "roofline": {"bound": "smem" if in_smem else "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_kmc_step": b_step}})
+        if key in counters:
+            out[-1]["cpu_port_single_core"] = {"value": counters[key][2], "unit": UNIT,
+                                               "note": "one replica on one host core, the `kmos benchmark` shape"}
         if fast is not None:
             out.append(fast)
     return out
