@@ -251,19 +251,19 @@ struct KbGenCtx {
             lo = c0;
         }
         const bool move = del_go && (int)t < nq;
-        if (add_go || move) {
-            const int idx = add_go ? nq : (int)t - 1;
-            const uint32_t val = add_go ? (ca2 >> 1) : last;
-            *list_at(lb + 2u * (uint32_t)idx) = (uint16_t)val;
-            if (add_go || idx >= lo) kb_sts16(wina + 2u * (uint32_t)(idx & 3), val);
-        }
+        // operands computed unconditionally, five predicated stores: no branch in the round's tail
+        const bool wr = add_go || move, upd = add_go || del_go;
+        const int idx = add_go ? nq : (int)t - 1;
+        const uint32_t val = add_go ? (ca2 >> 1) : last;
+        const bool wr_win = wr && (add_go || idx >= lo);
+        const int nq2 = add_go ? nq + 1 : nq - 1;
+        const int lo2 = add_go ? max(lo, nq - 3) : lo;
+        const uint32_t ent = add_go ? (tag | (uint32_t)(nq + 1)) : 0u;
+        if (wr) *list_at(lb + 2u * (uint32_t)idx) = (uint16_t)val;
+        if (wr_win) kb_sts16(wina + 2u * (uint32_t)(idx & 3), val);
         if (move) kb_sts16(plane + 2u * last, e);
-        if (add_go || del_go) {
-            kb_sts16(ea, add_go ? (tag | (uint32_t)(nq + 1)) : 0u);
-            const int nq2 = add_go ? nq + 1 : nq - 1;
-            const int lo2 = add_go ? max(lo, nq - 3) : lo;
-            kb_sts32(nsa, (uint32_t)nq2 | ((uint32_t)lo2 << 16));
-        }
+        if (upd) kb_sts16(ea, ent);
+        if (upd) kb_sts32(nsa, (uint32_t)nq2 | ((uint32_t)lo2 << 16));
         __syncwarp();
     }
 };
