@@ -419,8 +419,9 @@ __global__ void __launch_bounds__(M::MAX_THREADS) kb_gen_kernel(const KbGenParam
         double rng_a = 0.0, rng_b = 0.0;  // even lanes: (-log(ran_time), ran_proc); odd lanes: (ran_site, -)
 
         const int n_it = (int)my_steps;
-        for (int it = 0; it < n_it; ++it) {
-            if (!__any_sync(KB_FULL, act)) break;
+        bool alive = __any_sync(KB_FULL, act);  // warp-uniform: some group of this warp is still stepping
+        for (int it = 0; it < n_it && alive; ++it) {
+            bool stopped = false;               // this group stopped in this step (dead-lock): re-vote at the end
             const int sub = it & (BATCH - 1);
             if (sub == 0) {
                 // BATCH steps of uniforms at once: lane sl serves step kmc_step + sl/2, Philox slot sl&1
@@ -480,26 +481,23 @@ __global__ void __launch_bounds__(M::MAX_THREADS) kb_gen_kernel(const KbGenParam
 #pragma unroll
             for (int j = 1; j < PPL; ++j) acc[j] = __dadd_rn(acc[j - 1], pr[j]);
             const double total = __shfl_sync(KB_FULL, acc[PPL - 1], LPR - 1, LPR);  // the last lane has added every product
-            if (act && !(total > 0.0)) { status = KB_DEADLOCK; act = false; }
+            if (act && !(total > 0.0)) { status = KB_DEADLOCK; act = false; stopped = true; }
 
             const bool act_clk = act;  // the clock advances for this step (update_clocks below, behind the site read)
 
             // -- determine_procsite: first process whose accumulated rate exceeds ran_proc*total
-            const double value = __dmul_rn(ran_proc, total);
+            double value = __dmul_rn(ran_proc, total);
+            // value >= accum(P) (ran_proc*total rounded up to the total): the reference's search ends on the last
+            // entry and then walks left over entries that are >= their right neighbour (base.mpy:1316-1326),
+            // i.e. it returns the first process whose accumulated rate equals the total.  Searching for the
+            // largest double below the total finds exactly that process: no second pass, no branch.
+            if (!(value < total)) value = __longlong_as_double(__double_as_longlong(total) - 1LL);
             int pidx = 0;
 #pragma unroll
             for (int j = 0; j < PPL; ++j) pidx += __popc(__ballot_sync(KB_FULL, has[j] && !(value < acc[j])) & gmask);
-            if (__any_sync(KB_FULL, act && pidx >= P)) {
-                // value >= accum(P): the reference's search ends on the last entry and then walks left over
-                // entries that are >= their right neighbour (base.mpy:1316-1326)
-                int ge = 0;
-#pragma unroll
-                for (int j = 0; j < PPL; ++j) ge += __popc(__ballot_sync(KB_FULL, has[j] && acc[j] >= total) & gmask);
-                if (pidx >= P) pidx = P - ge;
-            }
-            if (!act) pidx = 0;
+            if (!act || pidx >= P) pidx = 0;
             const int nsel = (int)(nS[pidx] & 0xffffu);
-            if (act && nsel <= 0) { status = KB_DEADLOCK; act = false; }  // the clock has advanced: the step counts
+            if (act && nsel <= 0) { status = KB_DEADLOCK; act = false; stopped = true; }  // the clock has advanced: the step counts
             int k = (int)__dadd_rn(1.0, __dmul_rn(ran_site, (double)nsel));
             k = max(min(k, nsel), 1);
 
@@ -510,12 +508,13 @@ __global__ void __launch_bounds__(M::MAX_THREADS) kb_gen_kernel(const KbGenParam
             // -- update_clocks / update_integ_rate, issued behind the site read: they do not depend on it and
             // the division's latency disappears in the L2 round trip (+4 %)
             asm volatile("" : "+r"(cell));
-            if (act_clk) {
-                kmc_dt = neg_log_u / total;
-                kmc_time = __dadd_rn(kmc_time, kmc_dt);
+            {   // a stopped group divides by its zero total and discards the result: no branch
+                const double dt = neg_log_u / total;
+                kmc_dt = act_clk ? dt : kmc_dt;
+                kmc_time = act_clk ? __dadd_rn(kmc_time, dt) : kmc_time;
 #pragma unroll
-                for (int j = 0; j < PPL; ++j) integ[j] = __dadd_rn(integ[j], __dmul_rn(pr[j], kmc_dt));
-                ++nst;
+                for (int j = 0; j < PPL; ++j) integ[j] = act_clk ? __dadd_rn(integ[j], __dmul_rn(pr[j], dt)) : integ[j];
+                nst += act_clk ? 1 : 0;
             }
             // this lane's replace_species call (lanes 0..3 of the group), 0 = none
             const uint32_t wr = kb_ldc32(c.tab0 + (uint32_t)M::OFF_WR + 16u * (uint32_t)pidx + 4u * (uint32_t)(sl & 3));
@@ -530,11 +529,13 @@ __global__ void __launch_bounds__(M::MAX_THREADS) kb_gen_kernel(const KbGenParam
             for (int j = 0; j < PPL; ++j) cnt[j] += (act && pidx == PPL * sl + j) ? 1u : 0u;
             c.nbrow = c.nbT + cell * (2 * M::NOFF);
             // replace_species(site, old, new) (base.mpy:1187-1231): wr = column | (site-1) << 8 | old << 16 | new << 24
-            if (act && sl < 4 && wr != 0u) {
-                const uint32_t c2 = kb_ldc16(c.nbrow + (wr & 0xffu));
-                const uint32_t p = c.lat + c.lat_index(c2) + ((wr >> 8) & 0xffu);
-                if (kb_lds8(p) == ((wr >> 16) & 0xffu)) kb_sts8(p, wr >> 24);
-                else c.bad |= 2u << sl;
+            {   // every lane computes (an idle lane reads column 0 / site 1: valid), two predicated tails
+                const bool wv = act && sl < 4 && wr != 0u;
+                const uint32_t c2 = kb_ldc16(c.nbrow + __byte_perm(wr, 0u, 0x4440u));
+                const uint32_t p = c.lat + c.lat_index(c2) + __byte_perm(wr, 0u, 0x4441u);
+                const bool match = kb_lds8(p) == __byte_perm(wr, 0u, 0x4442u);
+                if (wv && match) kb_sts8(p, wr >> 24);
+                if (wv && !match) c.bad |= 2u << sl;
             }
             // rounds: the next round's operands are requested before the current round runs
             for (int r = 0; r < nr_max; ++r) {
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(M::MAX_THREADS) kb_gen_kernel(const KbGenParam
             }
             __syncwarp();  // lattice writes of an event without ops must be visible to the next step
 
-            if (__any_sync(KB_FULL, c.bad != 0)) {
+            if (__any_sync(KB_FULL, c.bad != 0 || stopped)) {
                 uint32_t gb = 0;  // OR of the group's flags
 #pragma unroll
                 for (int i = 0; i < 5; ++i)
@@ -571,6 +572,7 @@ __global__ void __launch_bounds__(M::MAX_THREADS) kb_gen_kernel(const KbGenParam
                     act = false;
                 }
                 c.bad = 0;
+                alive = __any_sync(KB_FULL, act);
             }
         }
         const long long kmc_step = step0 + nst;
