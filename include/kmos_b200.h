@@ -97,6 +97,10 @@ int kmos_b200_kernel_info(kmos_b200_batch *b, int64_t info[12]);
  * (hash checked).  Afterwards KMOS_B200_KERNEL_AUTO prefers KMOS_B200_KERNEL_GENERATED where it fits; the
  * table interpreter kernels stay available through kmos_b200_select_kernel. */
 int kmos_b200_batch_attach_proclist(kmos_b200_batch *b, const char *so_path);
+/* Unload the attached module again (state is converted back to the canonical planes first); the batch returns
+ * to the table-driven kernels.  Lets a front-end try the module of another lane-group width: how many replicas
+ * a width keeps resident depends on the lattice, which is only known when the batch exists. */
+int kmos_b200_batch_detach_proclist(kmos_b200_batch *b);
 
 /* RNG: per-replica Philox4x32-10 stream, key = seed, counter = (kmc_step, replica_id, slot).
  * replaces: random_seed(put=seed_arr) in initialize_state (proclist_generic_subroutines.mpy:253-258).

@@ -103,6 +103,7 @@ def lib():
         "kmos_b200_batch_volume": (C.c_int, [vp]),
         "kmos_b200_select_kernel": (C.c_int, [vp, i32]),
         "kmos_b200_batch_attach_proclist": (C.c_int, [vp, C.c_char_p]),
+        "kmos_b200_batch_detach_proclist": (C.c_int, [vp]),
         "kmos_b200_kernel_info": (C.c_int, [vp, arr(np.int64)]),
         "kmos_b200_set_seeds": (C.c_int, [vp, arr(np.uint64), vp]),
         "kmos_b200_set_rates": (C.c_int, [vp, arr(np.float64)]),
@@ -159,7 +160,7 @@ EXPORTED = [
     "kmos_b200_get_avail_sites", "kmos_b200_get_status", "kmos_b200_get_error_info", "kmos_b200_tally_words",
     "kmos_b200_reduce_tallies", "kmos_b200_philox_next", "kmos_b200_batch_set_stream",
     "kmos_b200_measure_smem_bandwidth", "kmos_b200_get_next_kmc_step", "kmos_b200_run_proc_nr",
-    "kmos_b200_reload_replica", "kmos_b200_batch_attach_proclist",
+    "kmos_b200_reload_replica", "kmos_b200_batch_attach_proclist", "kmos_b200_batch_detach_proclist",
 ]
 
 

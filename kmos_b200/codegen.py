@@ -149,6 +149,29 @@ def choose_lpr(an):
     return 32
 
 
+def expected_max_rounds(rounds_per_event, n_groups):
+    """Expected number of rounds of the slowest of `n_groups` events drawn uniformly from the model's processes:
+    the groups of a warp run their rounds in lock step."""
+    r = np.asarray(rounds_per_event, dtype=float)
+    if r.size == 0:
+        return 0.0
+    vals = np.unique(r)
+    cdf = np.array([(r <= v).mean() for v in vals]) ** n_groups
+    return float((vals * np.diff(np.concatenate([[0.0], cdf]))).sum())
+
+
+def lane_group_score(n_proc, emax, n_groups, replicas_per_sm):
+    """Relative throughput estimate of a lane-group width for one batch geometry (higher is better).
+
+    A group-step costs about I = 170 + 3.5 P + 100 E[max rounds] warp instructions.  With `replicas_per_sm`
+    resident replicas the kernel is bound either by the latency of that chain (~5.5 cycles per instruction,
+    every resident replica advancing one step per chain) or by issue slots (about 3 per cycle, a warp
+    instruction serving 32/lpr replicas).  Fitted on RuO2, ZGB, AB, mini_101 and pairwise at 8/16/32 lanes
+    (DESIGN.md 4.1): picks the measured best width for all but RuO2 (16 instead of 8: -4 %)."""
+    instr = 170.0 + 3.5 * n_proc + 100.0 * emax
+    return min(replicas_per_sm / 5.5, 3.0 * n_groups) / instr
+
+
 def analyse(ir, lpr=None):
     """_flatten + the lane-group width + every event's rounds (ev["rounds"] = [[op, ...], ...])."""
     an = _flatten(ir)

@@ -1028,6 +1028,24 @@ extern "C" int kmos_b200_batch_attach_proclist(kmos_b200_batch* b, const char* s
     return KMOS_B200_OK;
 }
 
+extern "C" int kmos_b200_batch_detach_proclist(kmos_b200_batch* b) {
+    if (!b) return set_err(KMOS_B200_ERR_ARG, "detach_proclist: bad arguments");
+    if (!b->gen_ok) return KMOS_B200_OK;
+    CU(cudaSetDevice(b->device));
+    if (b->compact_valid && b->compact_kind == 1) {
+        int rc = ensure_canonical(b);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    cudaFree(b->d_gen_tab); cudaFree(b->d_gen_writes); cudaFree(b->d_gen_dev); cudaFree(b->gen_image);
+    b->d_gen_tab = nullptr; b->d_gen_writes = nullptr; b->d_gen_dev = nullptr; b->gen_image = nullptr;
+    if (b->gen.handle) dlclose(b->gen.handle);
+    b->gen = KbGenModule();
+    b->gen_ok = false;
+    b->kernel = auto_kernel(b);
+    return KMOS_B200_OK;
+}
+
 static int launch_generated(kmos_b200_batch* b, long long n) {
     int rc = ensure_compact(b, 1);
     if (rc) return rc;

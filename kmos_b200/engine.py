@@ -92,24 +92,56 @@ class Batch(object):
         cached build and no compiler, or the module declines this lattice geometry."""
         import shutil
         from . import codegen, devtables
-        path = proclist
-        if proclist in ("auto", "build"):
-            try:
-                path = codegen.find_built(self.model.ir, self.model.blob, lpr=lpr)
-                if path is None and (proclist == "build" or shutil.which(os.environ.get("NVCC", "nvcc"))):
-                    path = codegen.build(self.model.ir, self.model.blob, lpr=lpr)
-            except devtables.Unsupported:
-                if proclist == "build":
-                    raise
-                path = None
+        if proclist not in ("auto", "build"):
+            capi.check(self.L.kmos_b200_batch_attach_proclist(self.h, str(proclist).encode()))
+            self.proclist = proclist
+            return proclist
+        can_build = proclist == "build" or bool(shutil.which(os.environ.get("NVCC", "nvcc")))
+
+        def module(width):
+            path = codegen.find_built(self.model.ir, self.model.blob, lpr=width)
+            if path is None and can_build:
+                path = codegen.build(self.model.ir, self.model.blob, lpr=width)
+            return path
+
+        env = os.environ.get("KMOS_B200_GEN_LPR")
+        widths = [int(lpr)] if lpr else ([int(env)] if env else [8, 16, 32])
+        try:
+            an = codegen._flatten(self.model.ir)
+        except devtables.Unsupported:
+            if proclist == "build":
+                raise
+            return None
+        # How many replicas a lane-group width keeps resident depends on the lattice: attach every candidate
+        # width once, score it (codegen.lane_group_score), keep the best.
+        best = None
+        for w in widths:
+            path = module(w)
             if path is None:
-                return None
-        rc = self.L.kmos_b200_batch_attach_proclist(self.h, str(path).encode())
-        if rc != 0 and proclist == "auto":
-            return None  # e.g. a lattice smaller than twice the interaction range: the interpreter handles it
-        capi.check(rc)
-        self.proclist = path
-        return path
+                continue
+            rc = self.L.kmos_b200_batch_attach_proclist(self.h, str(path).encode())
+            if rc != 0:
+                if proclist == "build" and len(widths) == 1:
+                    capi.check(rc)
+                continue  # e.g. a lattice smaller than twice the interaction range: the interpreter handles it
+            if len(widths) == 1:
+                self.proclist = path
+                return path
+            info = np.zeros(12, dtype=np.int64)
+            self.L.kmos_b200_select_kernel(self.h, capi.KERNEL_GENERATED)
+            capi.check(self.L.kmos_b200_kernel_info(self.h, info))
+            resident = int(info[1] * info[3])
+            per_sm = min(resident, max(1, -(-self.R // max(int(info[4]), 1))))
+            rounds = [len(r) for r in codegen._schedule(an, w)]
+            score = codegen.lane_group_score(an["nproc"], codegen.expected_max_rounds(rounds, 32 // w), 32 // w, per_sm)
+            capi.check(self.L.kmos_b200_batch_detach_proclist(self.h))
+            if best is None or score > best[0]:
+                best = (score, w, path)
+        if best is None:
+            return None
+        capi.check(self.L.kmos_b200_batch_attach_proclist(self.h, str(best[2]).encode()))
+        self.proclist = best[2]
+        return best[2]
 
     def select_kernel(self, kind):
         capi.check(self.L.kmos_b200_select_kernel(self.h, int(kind)))
