@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B of kernel switches on the headline workload: KMOS_B200_GEN_DEFS variants, LPR from $1
+# A/B of generated-kernel variants on the headline workload (how the round-2 experiments in DESIGN.md 4.1 were run):
+#   bash tools/gpu_ab.sh <lanes per replica> "<-D switches of variant 1>" "<variant 2>" ...
+# every variant is a separately generated + compiled module (KMOS_B200_GEN_DEFS is part of the cache key)
 mkdir -p gpurun_out
 L=${1:-16}
 shift
