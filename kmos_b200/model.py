@@ -29,12 +29,14 @@ class _Namespace(object):
 
 class KMC_Model(object):
     def __init__(self, model, size=20, n_replicas=1, seeds=None, parameters=None, device=0, kernel=capi.KERNEL_AUTO,
-                 random_seed=1, mu=None, cache_file=None):
+                 random_seed=1, mu=None, cache_file=None, replica_ids=None):
         """model: path of a rule-table JSON (what the exporter hook writes) or a parsed IR dict.
         parameters: dict of overrides, or a list of R dicts (one parameter point per replica).
         mu: chemical potentials for ``mu_<gas>`` tokens: a ``kmos.species``-compatible provider or a callable
         (gas, T, p) -> eV.  Default: the reference's kmos.species if importable, else the closed-form stand-in
-        of kmos_b200.rates with a MuStandinWarning (rate constants then differ from the reference's)."""
+        of kmos_b200.rates with a MuStandinWarning (rate constants then differ from the reference's).
+        replica_ids: the replicas' indices in the Philox counter (default 0..R-1); a sweep sharded over several
+        batches passes its global indices so that the shards reproduce the unsharded run."""
         self.ir = tables.load_ir(model) if isinstance(model, str) else model
         self.model = engine.Model(ir=self.ir)
         dim = self.ir["model_dimension"]
@@ -50,6 +52,7 @@ class KMC_Model(object):
         if seeds is None:
             seeds = np.uint64(random_seed) + np.arange(self.R, dtype=np.uint64)
         self.batch = engine.Batch(self.model, self.R, self.size[:dim].astype(np.int32), device=device, seeds=seeds,
+                                  replica_ids=replica_ids,
                                   rates=self._evaluate_rates(), lut=self._evaluate_lut(), kernel=kernel)
         self.species_names = list(self.ir["species"])
         self.site_names = list(self.ir["sites"])

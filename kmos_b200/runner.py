@@ -85,7 +85,7 @@ def _run_points(model_path, size, seeds, points, first_point, device, init_steps
     keys = (np.uint64(random_seed) + gid.astype(np.uint64))
     factory = model_factory or KMC_Model
     with factory(model_path, size=size, n_replicas=len(per_rep), parameters=per_rep, device=device,
-                 seeds=keys) as model:
+                 seeds=keys, replica_ids=gid.astype(np.uint32)) as model:
         model.do_steps(int(init_steps))
         model.get_atoms_all()
         rows = model.get_std_sampled_data_all(samples, int(sample_steps), tof_method="integ")

@@ -4,8 +4,9 @@ import numpy as np
 
 
 class FakeModel(object):
-    def __init__(self, model, size=20, n_replicas=1, parameters=None, device=0, seeds=None):
+    def __init__(self, model, size=20, n_replicas=1, parameters=None, device=0, seeds=None, replica_ids=None):
         self.params, self.seeds, self.device = parameters, np.asarray(seeds, dtype=np.uint64), device
+        assert np.array_equal(np.asarray(replica_ids, dtype=np.uint64) + np.uint64(7), self.seeds)  # global ids
         self.steps = 0
 
     def __enter__(self):
