@@ -164,12 +164,16 @@ def lane_group_score(n_proc, emax, n_groups, replicas_per_sm):
     """Relative throughput estimate of a lane-group width for one batch geometry (higher is better).
 
     A group-step costs about I = 170 + 3.5 P + 100 E[max rounds] warp instructions.  With `replicas_per_sm`
-    resident replicas the kernel is bound either by the latency of that chain (~5.5 cycles per instruction,
-    every resident replica advancing one step per chain) or by issue slots (about 3 per cycle, a warp
-    instruction serving 32/lpr replicas).  Fitted on RuO2, ZGB, AB, mini_101 and pairwise at 8/16/32 lanes
-    (DESIGN.md 4.1): picks the measured best width for all but RuO2 (16 instead of 8: -4 %)."""
+    resident replicas in w = replicas / groups warps the kernel is bound either by the latency of that chain --
+    2.3 + 0.2 w cycles per instruction (issue contention grows with the resident warps; below 8 warps per SM a
+    scheduler has nothing to overlap, hence the w/8 factor), every resident replica advancing one step per
+    chain -- or by issue slots (about 3 per cycle, a warp instruction serving 32/lpr replicas).  Fitted on
+    RuO2 (full and 2048-replica batches), ZGB, AB, mini_101 and pairwise at 8/16/32 lanes: it
+    picks the measured best width in all six cases."""
     instr = 170.0 + 3.5 * n_proc + 100.0 * emax
-    return min(replicas_per_sm / 5.5, 3.0 * n_groups) / instr
+    warps = replicas_per_sm / float(n_groups)
+    latency = replicas_per_sm / (2.3 + 0.2 * warps) * min(1.0, warps / 8.0)
+    return min(latency, 3.0 * n_groups) / instr
 
 
 def analyse(ir, lpr=None):

@@ -173,16 +173,17 @@ def _next(o):
 
 def test_lane_group_width_model():
     """codegen: rounds per lane-group width, the lock-step expectation and the score the engine ranks widths by
-    (measured best widths on B200: RuO2 20x20 8/16 within 4 %, ZGB 32x32 and pairwise 30x30 16, AB and
-    mini_101 20x20 8 -- DESIGN.md 4.1)."""
+    (measured best widths on B200: RuO2 20x20 8 for a full batch and 16 for a 2048-replica shard, ZGB 32x32 and
+    pairwise 30x30 16, AB and mini_101 20x20 8 -- DESIGN.md 4.1)."""
     from kmos_b200 import codegen
     assert codegen.expected_max_rounds([3, 3, 3], 4) == 3.0
     assert abs(codegen.expected_max_rounds([1, 3], 2) - 2.5) < 1e-12        # P(max = 1) = 1/4
     assert codegen.expected_max_rounds([], 2) == 0.0
-    measured_best = {"ruo2": ((32, 32, 24), (16, 8)), "zgb": ((24, 26, 24), (16,)), "pairwise": ((24, 24, 24), (16,)),
-                     "ab": ((64, 40, 24), (8,)), "mini_101": ((128, 40, 24), (8,))}
+    measured_best = {"ruo2": ((32, 32, 24), (8,)), "zgb": ((24, 26, 24), (16,)), "pairwise": ((24, 24, 24), (16,)),
+                     "ab": ((64, 40, 24), (8,)), "mini_101": ((128, 40, 24), (8,)),
+                     "ruo2 ": ((14, 14, 14), (16,))}      # a 2048-replica shard: 14 replicas per SM at any width
     for name, (resident, best) in measured_best.items():
-        ir, _blob, _info = load_model(name + "_local_smart")
+        ir, _blob, _info = load_model(name.strip() + "_local_smart")
         an = codegen._flatten(ir)
         scores = {}
         for w, reps in zip((8, 16, 32), resident):
