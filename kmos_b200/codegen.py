@@ -75,6 +75,8 @@ def _flatten(ir):
         raise Unsupported("more than 64 processes")
     if len(ir["species"]) > 16:
         raise Unsupported("more than 16 species")
+    if ir["spuck"] > 128:
+        raise Unsupported("more than 128 sites per cell")
     if ir.get("null_species", -1) >= 0:
         raise Unsupported("multi-lattice model (null species on the lattice)")
     classes, cls_of, member_of = devtables.exclusivity_classes(ir, proc_anchor)

@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(M::MAX_THREADS) kb_gen_kernel(const KbGenParam
             {   // every lane computes (an idle lane reads column 0 / site 1: valid), two predicated tails
                 const bool wv = act && sl < 4 && wr != 0u;
                 const uint32_t c2 = kb_ldc16(c.nbrow + __byte_perm(wr, 0u, 0x4440u));
-                const uint32_t p = c.lat + c.lat_index(c2) + __byte_perm(wr, 0u, 0x4441u);
+                const uint32_t p = c.lat + c.lat_index(c2) + (__byte_perm(wr, 0u, 0x4441u) & 0x7fu);
                 const bool match = kb_lds8(p) == __byte_perm(wr, 0u, 0x4442u);
                 if (wv && match) kb_sts8(p, wr >> 24);
                 if (wv && !match) c.bad |= 2u << sl;
@@ -729,8 +729,8 @@ static inline void kb_gen_fill_tables(const KbGenInfo& gi, const KbGenPlan& pl, 
             const uint32_t x = gi.writes[4 * p + i];  // off id | n << 8 | old << 16 | new << 24, 0 = none
             wrw[4 * p + i] = 0;
             if (!x) continue;
-            // old != new, so the word of a real write is never 0
-            wrw[4 * p + nw++] = (2u * (x & 255u)) | ((((x >> 8) & 255u) - 1u) << 8) | (x & 0xffff0000u);
+            // bit 15 marks a real write: a check-only call on species 0 of site 1 of column 0 would read as 0
+            wrw[4 * p + nw++] = (2u * (x & 255u)) | ((((x >> 8) & 255u) - 1u) << 8) | (x & 0xffff0000u) | 0x8000u;
         }
         evw[4 * p] = (uint32_t)gi.off_rd + 4u * (uint32_t)gi.events[p].first_round;
         evw[4 * p + 1] = (uint32_t)gi.events[p].n_rounds | ((uint32_t)nw << 8);

@@ -134,7 +134,22 @@ def flatten_event(ir, proc_index):
     for stmts, rb in seq:
         walk(stmts, rb, [])
         action[0] += 1
-    return base_n, writes, ops
+    # An event may touch one site twice -- the reference turns A -> B into take_A (A -> empty) followed by put_B
+    # (empty -> B), e.g. the predation step of examples/render_Lotka_Volterra_model.py.  The kernels apply an
+    # event's lattice writes concurrently, one per lane, so such a pair becomes one write: expected species of
+    # the first call (what replace_species checks first, base.mpy:1205), final species of the last.  The list
+    # operations in between keep their order and their view of the intermediate species (`known` above).
+    merged = []
+    for site, old, new in writes:
+        for w in merged:
+            if w[0] == site:
+                if w[2] != old:
+                    raise Unsupported("replace_species chain on one site does not connect")
+                w[2] = new
+                break
+        else:
+            merged.append([site, old, new])
+    return base_n, [tuple(w) for w in merged], ops
 
 
 def process_conditions(ir):

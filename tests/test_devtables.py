@@ -144,6 +144,7 @@ class EventModel(object):
     ("mini_101_local_smart", [3, 3], 2000),
     ("ruo2_local_smart", [20, 20], 1500),
     ("pairwise_local_smart", [8, 8], 2000),
+    ("pt111_local_smart", [7, 6], 2000), ("einsd_local_smart", [19], 1500),
 ])
 def test_event_tables_reproduce_avail_order(name, size, steps):
     ir, blob, info = load_model(name)
@@ -194,3 +195,20 @@ def test_lane_group_width_model():
     # the exclusivity classes are a minimum clique cover: RuO2 needs 6 planes, not first-fit's 7
     ir, _b, _i = load_model("ruo2_local_smart")
     assert len(codegen.analyse(ir)["classes"]) == 6
+
+
+def test_two_replace_species_calls_on_one_site_become_one_write():
+    """examples/render_Lotka_Volterra_model.py, AB_reaction*: the reference turns A -> B on one site into take_A
+    (A -> empty) followed by put_B (empty -> B).  The kernels apply an event's lattice writes concurrently, one per
+    lane, so the pair must reach them as one write (first expected species, last new species); the list
+    operations in between keep the intermediate species in view (found on the GPU in round 2: every replica
+    stopped with a species-mismatch status)."""
+    ir, _blob, _info = load_model("lotka_local_smart")
+    A, B = ir["species"].index("A"), ir["species"].index("B")
+    for p, name in enumerate(ir["procs"]):
+        _base_n, writes, ops = dt.flatten_event(ir, p)
+        sites = [tuple(w[0]) for w in writes]
+        assert len(set(sites)) == len(sites), name
+        if name.startswith("AB_reaction"):
+            assert [(old, new) for _s, old, new in writes] == [(A, B)], (name, writes)
+            assert len(ops) > 0

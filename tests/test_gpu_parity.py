@@ -30,6 +30,10 @@ SMEM_CASES = [
     ("hop3d_local_smart", [5, 6, 5], 7, [2000, 2000]),   # 3-d and 1-d lattices (no reference example has them)
     ("hop3d_local_smart", [9, 8, 7], 4, [3000]),
     ("hop1d_local_smart", [17], 6, [2000, 2000]),
+    # further examples of the reference (examples/render_{Lotka_Volterra_model,diffusion_model,sand_model,Pt_111,
+    # einsD}.py)
+    ("pt111_local_smart", [8, 7], 9, [3000, 3000]),
+    ("einsd_local_smart", [23], 9, [2000, 2000]),
 ]
 
 
@@ -118,6 +122,8 @@ LATINT_CASES = [
     ("ruo2_lat_int", [8, 8], 5, [1500, 1500]),
     ("pairwise_lat_int", [16, 16], 8, [2000, 2000]),
     ("pairwise_lat_int", [5, 3], 3, [1000]),
+    ("pt111_lat_int", [7, 6], 5, [2000, 2000]),
+    ("einsd_lat_int", [19], 5, [2000, 2000]),
 ]
 
 
@@ -201,6 +207,39 @@ def test_local_smart_lattice_too_large_for_shared_memory():
     next(gen)
     batch.do_steps(n)
     compare_batch(batch, next(gen), avail_replicas=(0, R - 1))
+    batch.close()
+
+
+@pytest.mark.parametrize("kernel", ["generated", "smem", "warp_hbm", "generic"])
+@pytest.mark.parametrize("name,size", [
+    ("lotka_local_smart", [12, 10]), ("diffusion_local_smart", [9, 9]), ("sand_local_smart", [10, 8]),
+    ("lotka_lat_int", [9, 8]), ("diffusion_lat_int", [8, 7]), ("sand_lat_int", [8, 8]),
+])
+def test_reference_examples_from_random_configurations(name, size, kernel):
+    """examples/render_{Lotka_Volterra_model,diffusion_model,sand_model}.py: nothing can happen on their default
+    lattice (the examples' users set a configuration first), so every replica starts from its own random
+    configuration (set_configuration + _adjust_database, kmos/run/__init__.py:1411-1457).  Replicas whose
+    populations die out must stop with the oracle's dead-lock status at the oracle's step."""
+    engine = _engine()
+    ir, blob, info = load_model(name)
+    if ir["backend"] == "lat_int" and kernel in ("generated", "smem"):
+        pytest.skip("local_smart kernels")
+    R = 7
+    rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + 2)
+    batch = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=rates, kernel=KINDS[kernel])
+    assert batch.kernel_info()["kernel_name"] == kernel
+    oracles = next(run_oracles(blob, size, rates, lut, seeds, []))
+    rng = np.random.RandomState(7)
+    spec = rng.randint(0, len(ir["species"]), (R, batch.volume)).astype(np.int32)
+    batch.set_configuration(spec)
+    for r, o in enumerate(oracles):
+        assert o.set_configuration(spec[r]) == 0
+    compare_batch(batch, oracles, avail_replicas=(0, R - 1))
+    for n in (700, 1800):
+        batch.do_steps(n)
+        for o in oracles:
+            o.do_steps(n)
+        compare_batch(batch, oracles, avail_replicas=(0, R - 1))
     batch.close()
 
 

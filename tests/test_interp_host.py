@@ -60,6 +60,11 @@ CASES = [
     ("hop3d_otf", [3, 5, 4], 3000),
     ("hop1d_local_smart", [17], 2000),
     ("hop1d_lat_int", [23], 2000),
+    # further reference examples (round 2): H/Pt(111) with two hollow sites per cell, the reference's 1-d model
+    # (Lotka-Volterra, diffusion and sand pile dead-lock from the default state: GPU parity runs them from
+    # random configurations, tests/test_gpu_parity.py)
+    ("pt111_local_smart", [8, 7], 3000), ("pt111_lat_int", [7, 6], 3000),
+    ("einsd_local_smart", [23], 2000), ("einsd_lat_int", [19], 2000),
 ]
 
 

@@ -218,6 +218,19 @@ MODELS = [
     ("pairwise_otf",
      lambda: project_from_render_script(os.path.join(REF, "examples/render_pairwise_interaction_otf.py")),
      ["otf"]),
+    # further examples of the reference (round 2): predator-prey on one site type with three species, a
+    # five-species diffusion model, the sand-pile model, H on Pt(111) with two hollow sites per cell, and the
+    # reference's own 1-d model
+    ("lotka", lambda: project_from_render_script(os.path.join(REF, "examples/render_Lotka_Volterra_model.py")),
+     ["local_smart", "lat_int"]),
+    ("diffusion", lambda: project_from_render_script(os.path.join(REF, "examples/render_diffusion_model.py")),
+     ["local_smart", "lat_int"]),
+    ("sand", lambda: project_from_render_script(os.path.join(REF, "examples/render_sand_model.py")),
+     ["local_smart", "lat_int"]),
+    ("pt111", lambda: project_from_render_script(os.path.join(REF, "examples/render_Pt_111.py")),
+     ["local_smart", "lat_int"]),
+    ("einsd", lambda: project_from_render_script(os.path.join(REF, "examples/render_einsD.py")),
+     ["local_smart", "lat_int"]),
 ]
 
 
