@@ -145,6 +145,7 @@ class EventModel(object):
     ("ruo2_local_smart", [20, 20], 1500),
     ("pairwise_local_smart", [8, 8], 2000),
     ("pt111_local_smart", [7, 6], 2000), ("einsd_local_smart", [19], 1500),
+    ("multidentate_local_smart", [9, 8], 2000),
 ])
 def test_event_tables_reproduce_avail_order(name, size, steps):
     ir, blob, info = load_model(name)

@@ -34,6 +34,7 @@ SMEM_CASES = [
     # einsD}.py)
     ("pt111_local_smart", [8, 7], 9, [3000, 3000]),
     ("einsd_local_smart", [23], 9, [2000, 2000]),
+    ("multidentate_local_smart", [9, 8], 9, [3000, 3000]),   # examples/multidentate.py: 2- and 4-site species
 ]
 
 
@@ -124,6 +125,7 @@ LATINT_CASES = [
     ("pairwise_lat_int", [5, 3], 3, [1000]),
     ("pt111_lat_int", [7, 6], 5, [2000, 2000]),
     ("einsd_lat_int", [19], 5, [2000, 2000]),
+    ("multidentate_lat_int", [8, 7], 5, [2000, 2000]),
 ]
 
 
@@ -172,6 +174,7 @@ OTF_CASES = [
     ("hop3d_otf", [5, 6, 5], 5, [1500, 1500]),
     ("ruo2default_otf", [8, 7], 5, [1500, 1500]),   # the reference's committed otf export: 36 processes, 2 sites/cell
     ("intzgb_otf", [10, 9], 6, [2000, 2000]),        # interacting ZGB: bystander-dependent rates (1150 LUT entries)
+    ("multidentate_otf", [8, 7], 5, [2000, 2000]),
 ]
 
 

@@ -65,6 +65,9 @@ CASES = [
     # random configurations, tests/test_gpu_parity.py)
     ("pt111_local_smart", [8, 7], 3000), ("pt111_lat_int", [7, 6], 3000),
     ("einsd_local_smart", [23], 2000), ("einsd_lat_int", [19], 2000),
+    # multidentate adsorbates (examples/multidentate.py): one species spans two and four sites
+    ("multidentate_local_smart", [9, 8], 3000), ("multidentate_lat_int", [8, 7], 3000),
+    ("multidentate_otf", [8, 7], 3000),
 ]
 
 

@@ -231,6 +231,9 @@ MODELS = [
      ["local_smart", "lat_int"]),
     ("einsd", lambda: project_from_render_script(os.path.join(REF, "examples/render_einsD.py")),
      ["local_smart", "lat_int"]),
+    # multidentate adsorbates: species that occupy two and four sites at once
+    ("multidentate", lambda: project_from_render_script(os.path.join(REF, "examples/multidentate.py")),
+     ["local_smart", "lat_int", "otf"]),
 ]
 
 
