@@ -14,7 +14,11 @@ _overrides = {}
 
 
 def __dir__():
-    return sorted(["update_user_parameter", "update_chempot"] + [n.lower() for n in rt.RT.ir.get("userpar", [])])
+    procs = [p.lower() for p in rt.RT.ir["procs"]]
+    return sorted(["update_user_parameter", "get_user_parameter"] +
+                  (["update_chempot"] if rt.RT.ir.get("chempots") else []) +
+                  [n.lower() for n in rt.RT.ir.get("userpar", []) + rt.RT.ir.get("chempots", [])] +
+                  ["byst_" + p for p in procs] + ["rate_" + p for p in procs])
 
 
 def _send():
@@ -31,12 +35,36 @@ def update_user_parameter(index, value):
     _send()
 
 
-def update_chempot(index, value):
-    raise NotImplementedError("chemical potentials are tabulated from T and p by kmos_b200.otf")
+def get_user_parameter(index):
+    """val = userpar(param) (kmos/io/__init__.py:2766-2774)."""
+    from kmos_b200 import otf
+    return float(otf.user_parameters(rt.RT.ir, _overrides)[0][int(index) - 1])
+
+
+def _update_chempot(index, value):
+    """chempots(index) = val: the value kmos.run.set_rate_constants evaluated replaces the tabulated one."""
+    _overrides[rt.RT.ir["chempots"][int(index) - 1]] = float(value)
+    _send()
 
 
 def __getattr__(name):
-    names = [n.lower() for n in rt.RT.ir.get("userpar", [])]
-    if name.lower() in names:
-        return names.index(name.lower()) + 1
+    # the generated module has update_chempot only when the model uses chemical potentials
+    # (kmos/io/__init__.py:2776-2786); kmos.run probes for it with hasattr
+    if name == "update_chempot" and rt.RT.ir.get("chempots"):
+        return _update_chempot
+    low = name.lower()
+    if low.startswith("byst_") or low.startswith("rate_"):
+        # byst_<proc>: names of the bystander counters; rate_<proc>(nr_vars): the rate for a given environment
+        by_lower = {p.lower(): p for p in rt.RT.ir["procs"]}
+        proc = by_lower.get(low[5:])
+        if proc is None:
+            raise AttributeError(name)
+        if low.startswith("byst_"):
+            return {k.lower(): v for k, v in rt.RT.ir.get("byst", {}).items()}.get(proc.lower(), "")
+        from kmos_b200 import otf
+        return otf.rate_function(rt.RT.ir, proc, rt.batch().rates[0], _overrides)
+    for names in (rt.RT.ir.get("userpar", []), rt.RT.ir.get("chempots", [])):
+        low = [n.lower() for n in names]
+        if name.lower() in low:
+            return low.index(name.lower()) + 1
     raise AttributeError(name)

@@ -714,6 +714,13 @@ def _parse_pars(path, env, ir):
     ir["userpar"] = [n for n, _ in userpar[:n_userpar]]
     ir["chempots"] = [n for n, _ in userpar[n_userpar:n_userpar + n_chempots]]
     ir["pars_constants"] = fconsts
+    # byst_<proc>: the names of gr_<proc>'s nr_vars counters, in order (kmos/io/__init__.py:2842-2848); the
+    # front-end reads them back to label rate_<proc>'s argument (kmos/run/__init__.py:1868-1899)
+    ir["byst"] = {}
+    for ln in lines:
+        m = re.match(r'^character\(len=\d+\)\s*,\s*parameter\s*,\s*public\s*::\s*byst_(\w+)\s*=\s*"(.*)"$', ln)
+        if m:
+            ir["byst"][m.group(1)] = " ".join(m.group(2).split())
     routines = _routines(lines)
     ir["rate_expr"] = {}
     for name, (kind, args, body) in routines.items():

@@ -77,16 +77,25 @@ def fortran_expr_to_callable(expr, proc_ids, userpar_ids, chempot_ids, constants
 
 
 def user_parameters(ir, overrides=None):
-    """userpar(:) / chempots(:) values in the order of the generated proclist_pars module."""
+    """userpar(:) / chempots(:) values in the order of the generated proclist_pars module.  `overrides` maps
+    parameter names to new values; an entry under a chemical potential's own name (``mu_<species>``, what
+    proclist_pars.update_chempot receives from kmos.run.set_rate_constants) is taken as that potential."""
     params = {k: dict(v) for k, v in ir["parameters"].items()}
+    given_mu = {}
     for k, v in (overrides or {}).items():
-        params.setdefault(k, {})["value"] = v
+        if k in ir.get("chempots", []):
+            given_mu[k] = float(v)
+        else:
+            params.setdefault(k, {})["value"] = v
     # first item of space-separated values: the reference does the same for its deprecated 'lattice_size'
     # parameter (kmos/run/__init__.py:2417-2428)
     userpar = [evaluate_rate_expression(str(params[name]["value"]).split(" ")[0], params)
                for name in ir.get("userpar", [])]
     chempots = []
     for name in ir.get("chempots", []):
+        if name in given_mu:
+            chempots.append(given_mu[name])
+            continue
         species = name[len("mu_"):]
         chempots.append(standin_mu(species, evaluate_rate_expression(str(params["T"]["value"]), params),
                                    evaluate_rate_expression(str(params["p_" + species]["value"]), params)))
@@ -123,6 +132,20 @@ def build_lut_batch(ir, info, rates, overrides_list=None):
                 stride *= r
             lut[:, g["lut_offset"] + idx] = f(cols, userpar, chempots, nv)
     return lut
+
+
+def rate_function(ir, proc, rates, overrides=None):
+    """``proclist_pars.rate_<proc>`` as a Python callable of nr_vars (kmos/io/__init__.py:3000-3122): the user
+    expression with the current rate constants, user parameters and chemical potentials bound."""
+    proc_ids = {p.lower(): i + 1 for i, p in enumerate(ir["procs"])}
+    userpar_ids = {n: i for i, n in enumerate(ir.get("userpar", []))}
+    chempot_ids = {n: i for i, n in enumerate(ir.get("chempots", []))}
+    userpar, chempots = user_parameters(ir, overrides)
+    by_lower = {k.lower(): v for k, v in ir["rate_expr"].items()}
+    f = fortran_expr_to_callable(by_lower[proc.lower()], proc_ids, userpar_ids, chempot_ids,
+                                 ir.get("pars_constants", {}))
+    rates = [float(x) for x in rates]
+    return lambda nr_vars=(): f(rates, userpar, chempots, [int(v) for v in nr_vars])
 
 
 def build_lut(ir, info, rates, overrides=None):

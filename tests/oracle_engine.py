@@ -39,6 +39,11 @@ class OracleBatch(object):
         self._rates[int(proc) - 1] = float(rate)
         self.o.set_rates(self._rates)
 
+    def set_otf_lut(self, lut):
+        """kmos_b200_set_otf_lut: new rate table + recalculate_rates_matrix (include/kmos_b200.h)."""
+        self.o.set_lut(np.asarray(lut, dtype=np.float64).reshape(-1))
+        self.o.recalculate_rates_matrix()
+
     def set_kmc_time(self, t):
         self.o.set_kmc_time(float(np.asarray(t).reshape(-1)[0]))
 

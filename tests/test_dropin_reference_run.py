@@ -32,9 +32,14 @@ sys.path[:0] = [os.path.join(repo, "kmos_b200", "dropin"), export_dir, os.path.j
 import numpy as np
 import kmos.types, kmos.io
 from kmos_b200 import export
-pt = kmos.types.Project()
-with open(os.path.join(ref, "tests", "test_run", "AB_model.ini")) as f:
-    pt.import_ini_file(f)
+if mode == "bystanders":   # examples/render_pairwise_interaction_otf.py: a desorption rate that depends on nr_CO_1nn
+    sys.path.insert(0, os.path.join(repo, "tools"))
+    import make_fixtures
+    pt = make_fixtures.project_from_render_script(os.path.join(ref, "examples", "render_pairwise_interaction_otf.py"))
+else:
+    pt = kmos.types.Project()
+    with open(os.path.join(ref, "tests", "test_run", "AB_model.ini")) as f:
+        pt.import_ini_file(f)
 export.export_source(pt, export_dir, code_generator=backend)   # the reference's exporter + model_tables.json
 os.chdir(export_dir)
 
@@ -48,10 +53,36 @@ _runtime.batch_factory = lambda ir, size, seed, layer: oracle_engine.OracleBatch
 import kmos.run                                           # UNMODIFIED reference front-end
 assert kmos.run.base is kmc_model.base and kmos.run.settings is not None
 out = {}
-with kmos.run.KMC_Model(print_rates=False, banner=False) as model:
+with kmos.run.KMC_Model(print_rates=False, banner=False, size=(8 if mode == "bystanders" else None)) as model:
     out["size"] = [int(x) for x in model.size]
     out["backend"] = model.get_backend()
-    if mode == "golden":
+    if mode == "bystanders":
+        # proclist_pars.byst_<proc> / rate_<proc>(nr_vars) behind KMC_Model.rate_constants (run/__init__.py:1851-1899)
+        rc = model.rate_constants
+        out["byst"] = rc.bystanders(pattern="CO_desorption", interactive=False)
+        out["rate0"] = rc._rate("CO_desorption")
+        out["rate2"] = rc._rate("CO_desorption", nr_CO_1nn=2)
+        out["base_rate"] = float(model.base.get_rate(model.proclist.co_desorption))
+        model.do_steps(3000)
+        # the live rates_matrix holds rate_<proc>(environment) for every registered (proc, site)
+        b = _runtime.batch()
+        p = int(model.proclist.co_desorption)
+        row = b.o.rates_matrix_row(p)
+        n = int(b.o.nr_of_sites[p - 1])
+        vals = sorted(set(round(float(v), 6) for v in row[:n]))
+        table = sorted(set(round(rc._rate("CO_desorption", nr_CO_1nn=k), 6) for k in range(5)))
+        out["row_in_table"] = all(v in table for v in vals) and n > 0
+        # a parameter change goes through update_user_parameter + recalculate_rates_matrix
+        before = rc._rate("CO_desorption", nr_CO_1nn=1)
+        model.parameters.E_CO_nn = 0.05
+        out["rate_changed"] = rc._rate("CO_desorption", nr_CO_1nn=1) != before
+        model.do_steps(2000)
+        out["kmc_step"] = int(model.base.get_kmc_step())
+        row = b.o.rates_matrix_row(p)
+        n = int(b.o.nr_of_sites[p - 1])
+        table = sorted(set(round(rc._rate("CO_desorption", nr_CO_1nn=k), 6) for k in range(5)))
+        out["row_in_new_table"] = all(round(float(v), 6) in table for v in row[:n]) and n > 0
+    elif mode == "golden":
         procs_sites = []
         for i in range(10000):
             proc, site = model.get_next_kmc_step()
@@ -78,6 +109,34 @@ with kmos.run.KMC_Model(print_rates=False, banner=False) as model:
         model.do_steps(500)
         out["kmc_step_end"] = int(model.base.get_kmc_step())
         out["avail_ok"] = model.base.get_avail_site(1, 1, 1) >= 0
+        # the reporting and editing helpers of the front-end, all on the f2py-shaped getters
+        out["coverages"] = model.print_coverages(to_stdout=False)
+        out["procstat_txt"] = model.print_procstat(to_stdout=False)
+        out["kmc_state"] = model.print_kmc_state(to_stdout=False)
+        out["accum"] = model.print_accum_rate_summation(to_stdout=False)
+        out["avail_proc1"] = len(model.get_avail(1))
+        out["nr_of_sites1"] = int(model.base.get_nrofsites(1))
+        out["nr2site"] = [str(x) for x in model.nr2site(5)]
+        name0 = model.rate_constants.names()[0]
+        model.rate_constants.set(name0, 12.5)
+        out["rate_set"] = float(model.base.get_rate(1))   # set() addresses processes by sorted position
+        model.parameters.T = 550
+        model.do_steps(300)
+        model.dump_config("cfg_test")
+        lat_before = np.array(model._get_configuration())
+        step_before = int(model.base.get_kmc_step())
+        model.do_steps(300)
+        model.load_config("cfg_test")
+        out["load_config_ok"] = bool(np.array_equal(np.array(model._get_configuration()), lat_before))
+        model.double()
+        out["size_doubled"] = [int(x) for x in model.size]
+        tiled = np.array(model._get_configuration())
+        out["double_tiles"] = bool(np.array_equal(tiled[:lat_before.shape[0], :lat_before.shape[1]], lat_before) and
+                                   np.array_equal(tiled[lat_before.shape[0]:, lat_before.shape[1]:], lat_before))
+        model.do_steps(300)
+        out["kmc_step_doubled"] = int(model.base.get_kmc_step())
+        model.reset()
+        out["kmc_step_reset"] = int(model.base.get_kmc_step())
 print("RESULT " + json.dumps(out))
 '''
 
@@ -102,7 +161,18 @@ def test_reference_test_run_loop_reproduces_the_golden_log(tmp_path):
     assert np.array_equal(np.asarray(out["procs_sites"]), ref)
 
 
-@pytest.mark.parametrize("backend", ["local_smart", "lat_int"])
+def test_otf_bystander_rates_through_the_unmodified_front_end(tmp_path):
+    """proclist_pars of an otf model with a bystander-dependent rate: byst_<proc>, rate_<proc>(nr_vars),
+    update_user_parameter and recalculate_rates_matrix as kmos.run uses them."""
+    out = _run(tmp_path, "otf", "bystanders")
+    assert out["backend"] == "otf" and out["size"] == [8, 8]
+    assert "nr_CO_1nn" in out["byst"]
+    assert out["rate0"] == pytest.approx(out["base_rate"], rel=1e-12) and out["rate2"] != out["rate0"]
+    assert out["row_in_table"] and out["rate_changed"] and out["row_in_new_table"]
+    assert out["kmc_step"] == 5000
+
+
+@pytest.mark.parametrize("backend", ["local_smart", "lat_int", "otf"])
 def test_unmodified_kmc_model_front_end_runs_on_the_dropin(tmp_path, backend):
     out = _run(tmp_path, backend, "api")
     assert out["backend"] == backend
@@ -112,3 +182,10 @@ def test_unmodified_kmc_model_front_end_runs_on_the_dropin(tmp_path, backend):
     assert out["header"].startswith("#") and out["header"].rstrip().endswith("kmc_time simulated_time kmc_steps")
     assert len(out["row"].split()) == len(out["header"].split())
     assert out["put_ok"] and out["avail_ok"] and out["kmc_step_end"] == 10000 + 2000 + 1000
+    assert "default_a" in out["coverages"] and "A_adsorption" in out["procstat_txt"]
+    assert "kmc steps" in out["kmc_state"] and "A_adsorption" in out["accum"]
+    assert out["avail_proc1"] == out["nr_of_sites1"] and out["nr2site"][3] == "default_a"
+    assert out["rate_set"] == 12.5
+    assert out["load_config_ok"]
+    assert out["size_doubled"] == [40, 40] and out["double_tiles"]
+    assert out["kmc_step_doubled"] >= 300 and out["kmc_step_reset"] == 0
