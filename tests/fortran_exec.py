@@ -276,7 +276,7 @@ class FortranModel(object):
                     self.routines[name] = r
                 i = j + 1
                 continue
-            m = re.match(r"^(integer|real)[^:]*::\s*(\w+)\s*=\s*([-+]?[\w.]+)$", s)
+            m = re.match(r"^(integer|real)[^:]*::\s*(\w+)\s*=\s*([-+]?[\w.]+(?:[-+]\d+)?)$", s)
             if m and "dimension" not in s:
                 try:
                     self.constants[m.group(2)] = int(m.group(3))
@@ -298,24 +298,32 @@ class FortranModel(object):
         """process number -> name, from run_proc_nr's `case(<name>)` labels (proclist.f90)."""
         out = {}
         for s in self.routines["run_proc_nr"].src:
-            m = re.match(r"^case\s*\((\w+)\)$", s)
-            if m and m.group(1) in self.constants:
-                out[self.constants[m.group(1)]] = m.group(1)
+            m = re.match(r"^case\s*\(([\w\s,]+)\)$", s)   # lat_int: one case lists a whole process group
+            for label in (m.group(1).split(",") if m else []):
+                label = label.strip()
+                if label in self.constants:
+                    out[self.constants[label]] = label
         return out
 
     def userpar_names(self):
         """names of userpar(:) in index order (proclist_pars.f90: `integer, public :: <name> = <index>`)."""
+        return [n for n, _i in self.index_declarations()[0]]
+
+    def index_declarations(self):
+        """([(name, index)] of userpar(:), [(name, index)] of chempots(:)): the index constants of
+        proclist_pars.f90 in declaration order; the chemical potentials restart at 1."""
         with open(os.path.join(self.path, "proclist_pars.f90")) as fh:
             text = [ln.lower() for ln in _logical_lines(fh.read())]
-        out = {}
-        started = False
+        groups = [[]]
         for ln in text:
             if ln.startswith("contains"):
                 break
             m = re.match(r"^integer\(kind=iint\), public :: (\w+) = (\d+)$", ln)
             if m:
-                out[int(m.group(2))] = m.group(1)
-        return [out[i] for i in sorted(out)]
+                if groups[-1] and int(m.group(2)) <= groups[-1][-1][1]:
+                    groups.append([])
+                groups[-1].append((m.group(1), int(m.group(2))))
+        return groups[0], (groups[1] if len(groups) > 1 else [])
 
 
 class Executor(object):
@@ -527,10 +535,17 @@ class Executor(object):
                     self.call(st[1], [eval(a, g, env) for a in st[2]])
             elif k == "select":
                 v = eval(st[1], g, env)
+                # `case default` is taken only when no other label matches, wherever it stands in the text
+                # (the lat_int generator writes it in front of the last label)
+                chosen = None
                 for keys, body in st[2]:
-                    if keys is None or any(eval(c, g, env) == v for c in keys):
-                        self._run(body, env)
+                    if keys is not None and any(eval(c, g, env) == v for c in keys):
+                        chosen = body
                         break
+                if chosen is None:
+                    chosen = next((body for keys, body in st[2] if keys is None), None)
+                if chosen is not None:
+                    self._run(chosen, env)
             elif k == "if":
                 self._run(st[2] if eval(st[1], g, env) else st[3], env)
             elif k == "assign":

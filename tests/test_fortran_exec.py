@@ -83,3 +83,123 @@ def test_fortran_text_executed_directly_matches_the_oracle(dirname, backend, siz
         compare("after %d events" % done)
     assert ex.kmc_step == o.kmc_step == n_events
     assert sum(ex.procstat) == n_events
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The same check on Fortran exported here, by the unmodified reference exporter, for the models of the BASELINE
+# configurations (B: ZGB, D: pairwise interaction lat_int, E: pairwise interaction otf) and for further examples.
+FRESH = [
+    # builder name in tools/make_fixtures.MODELS, backend, lattice, events
+    ("pairwise", "lat_int", [7, 6], 6000),        # config D: 3 + 2^4 processes, nli trees over five sites
+    ("pairwise_otf", "otf", [7, 6], 6000),        # config E: desorption rate from nr_CO_1nn
+    ("zgb", "local_smart", [8, 7], 6000),         # config B
+    ("zgb", "lat_int", [8, 7], 6000),
+    ("mini_101", "otf", [6, 5], 4000),            # config A's model on the other two backends
+    ("mini_101", "lat_int", [6, 5], 4000),
+    ("ab", "lat_int", [7, 7], 6000),
+    # ("ab", "otf") is left out: the AB model has a parameter and a species both called A, which proclist_pars
+    # and proclist_constants would both declare -- ambiguous in real Fortran (the reference's own otf test run
+    # never compiles it: tests/test_run/test_run.py re-imports the cached local_smart module)
+    ("hop3d", "lat_int", [4, 3, 5], 5000),        # z offsets
+    ("hop3d", "otf", [3, 5, 4], 5000),
+    ("hop1d", "lat_int", [23], 4000),
+    ("multidentate", "lat_int", [8, 7], 5000),    # species spanning two and four sites
+    ("multidentate", "otf", [8, 7], 5000),
+    ("pt111", "lat_int", [7, 6], 5000),           # two hollow sites per cell
+    ("einsd", "lat_int", [19], 4000),
+]
+
+EXPORT_DRIVER = r'''
+import os, sys
+repo, out = sys.argv[1:3]
+sys.path.insert(0, os.path.join(repo, "tools"))
+import make_fixtures as mf            # ase shim + JANAF stub + the reference on sys.path
+import kmos.io
+builders = {name: b for name, b, _ in mf.MODELS}
+for item in sys.argv[3:]:
+    name, backend = item.split(":")
+    d = os.path.join(out, "%s_%s" % (name, backend))
+    os.makedirs(d)
+    try:
+        kmos.io.export_source(builders[name](), d, code_generator=backend)
+    except Exception as e:             # write_settings is the last step; the Fortran is complete by then
+        print("settings:", name, backend, str(e).splitlines()[0][:80])
+print("EXPORTED")
+'''
+
+
+@pytest.fixture(scope="module")
+def fresh_exports(tmp_path_factory):
+    import subprocess
+    import sys
+    out = tmp_path_factory.mktemp("fresh_exports")
+    script = out / "driver.py"
+    script.write_text(EXPORT_DRIVER)
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    items = sorted(set("%s:%s" % (n, b) for n, b, _s, _e in FRESH))
+    p = subprocess.run([sys.executable, str(script), repo, str(out)] + items, capture_output=True, text=True,
+                       timeout=900)
+    assert p.returncode == 0 and "EXPORTED" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    return str(out)
+
+
+def _project_parameters(export_root, name, backend):
+    """{parameter: {"value": ..}} from the kmc_settings.py the reference exporter wrote next to the Fortran."""
+    ns = {}
+    with open(os.path.join(export_root, "%s_%s" % (name, backend), "kmc_settings.py")) as fh:
+        exec(compile(fh.read(), "kmc_settings.py", "exec"), ns)
+    return {k: {"value": v["value"]} for k, v in ns["parameters"].items()}
+
+
+@pytest.mark.parametrize("name,backend,size,n_events", FRESH)
+def test_fresh_exports_executed_directly_match_the_oracle(fresh_exports, name, backend, size, n_events):
+    path = os.path.join(fresh_exports, "%s_%s" % (name, backend))
+    fm = fortran_exec.FortranModel(path)
+    assert fm.backend == backend
+    ir = fortran_ir.parse_export_dir(path, backend)
+    P = len(ir["procs"])
+    assert fm.nr_of_proc == P and [fm.proc_names[i + 1] for i in range(P)] == [p.lower() for p in ir["procs"]]
+    rng = np.random.RandomState(len(name) + 3 * len(backend))
+    rates = np.exp(rng.uniform(-1.0, 1.0, P))
+    userpar = chempots = lut = None
+    if backend == "otf":
+        par_decl, mu_decl = fm.index_declarations()
+        assert [n.lower() for n in ir.get("userpar", [])] == [n for n, _ in par_decl]
+        assert [n.lower() for n in ir.get("chempots", [])] == [n for n, _ in mu_decl]
+        # the model's own parameter values (T, energies: random ones overflow the Arrhenius factors); the
+        # chemical potentials are inputs on both sides
+        sys_path_meta = _project_parameters(fresh_exports, name, backend)
+        ir["parameters"] = sys_path_meta
+        userpar = [float(v) for v in otf_mod.user_parameters(ir, {c: 0.0 for c in ir.get("chempots", [])})[0]]
+        chempots = [float(v) for v in -np.exp(rng.uniform(-0.4, 0.4, len(ir.get("chempots", []))))]
+    blob, info = tables.build_blob(ir)
+    if backend == "otf":
+        overrides = dict(zip(ir.get("chempots", []), chempots))
+        lut = otf_mod.build_lut(ir, info, rates, overrides)
+    seed, replica = 99, 3
+    o = oracle.Oracle(blob, size, seed=seed, replica=replica, rates=rates, lut=lut)
+    ex = fortran_exec.Executor(fm, size, rates, seed, replica, oracle.philox_step, userpar=userpar, chempots=chempots,
+                               layer=ir["layers"][ir["default_layer"]].lower() if "layers" in ir else None)
+
+    def compare(tag):
+        assert np.array_equal(np.asarray(ex.lattice), o.lattice), "lattice differs %s" % tag
+        assert np.array_equal(np.asarray(ex.nr_of_sites[1:]), o.nr_of_sites), "nr_of_sites differs %s" % tag
+        assert np.array_equal(ex.avail_sites_array(), o.avail_sites), "avail_sites differ %s" % tag
+        assert np.array_equal(np.asarray(ex.procstat[1:]), o.procstat), "procstat differs %s" % tag
+        if o.kmc_time > 0:
+            assert abs(ex.kmc_time - o.kmc_time) <= 1e-12 * o.kmc_time, tag
+        if backend == "otf":
+            for p in range(1, P + 1):
+                n = ex.nr_of_sites[p]
+                np.testing.assert_allclose(np.asarray(ex.rates_matrix[p][1:n + 1]), o.rates_matrix_row(p)[:n], rtol=0,
+                                           atol=0, err_msg="rates_matrix row %d %s" % (p, tag))
+
+    compare("after initialize_state")
+    done = 0
+    while done < n_events:
+        for _ in range(1000):
+            ex.step()
+        assert o.do_steps(1000) == 0
+        done += 1000
+        compare("after %d events" % done)
+    assert ex.kmc_step == o.kmc_step == n_events

@@ -86,3 +86,5 @@ if __name__ == "__main__":
         perf([("ruo2_local_smart", [20, 20], 16384, 5000)])
     if "ruo2gen" in what:
         perf([("ruo2_local_smart", [20, 20], 16384, 5000)], kernels=("generated",))
+    if "zgb" in what:   # config B on the generated kernel; KMOS_B200_GEN_LPR=8|16|32 picks the lane-group width
+        perf([("zgb_local_smart", [64, 64], 4096, 4000)], kernels=("generated", "auto"))
