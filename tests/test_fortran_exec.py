@@ -93,6 +93,9 @@ FRESH = [
     ("pairwise", "lat_int", [7, 6], 6000),        # config D: 3 + 2^4 processes, nli trees over five sites
     ("pairwise_otf", "otf", [7, 6], 6000),        # config E: desorption rate from nr_CO_1nn
     ("zgb", "local_smart", [8, 7], 6000),         # config B
+    ("ruo2", "local_smart", [6, 5], 6000),        # config C, the headline model (examples/render_co_oxidation_ruo2.py)
+    ("ruo2", "lat_int", [6, 5], 6000),
+    ("pairwise", "local_smart", [7, 6], 5000),
     ("zgb", "lat_int", [8, 7], 6000),
     ("mini_101", "otf", [6, 5], 4000),            # config A's model on the other two backends
     ("mini_101", "lat_int", [6, 5], 4000),
