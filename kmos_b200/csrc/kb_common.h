@@ -142,10 +142,20 @@ KB_HD int kb_imod(int a, int n) {
 }
 
 // lattice.mpy:146-168 calculate_lattice2nr, split into cell index (0-based) and site type (1-based)
+// a mod n for a coordinate plus a small offset: one conditional add or subtract in the usual case (the reference's
+// lattice2nr table covers [-L, 2L) and nothing else, lattice.mpy:121-132), the division only beyond it
+KB_HD int kb_wrap(int a, int n) {
+    if ((unsigned)a >= (unsigned)n) {
+        a = a < 0 ? a + n : a - n;
+        if ((unsigned)a >= (unsigned)n) a = kb_imod(a, n);
+    }
+    return a;
+}
+
 KB_HD int kb_cell_of(const KbModelView& m, const KbGeom& g, int x, int y, int z) {
-    int c = kb_imod(x, g.size[0]);
-    if (m.dim >= 2) c += g.size[0] * kb_imod(y, g.size[1]);
-    if (m.dim >= 3) c += g.size[0] * g.size[1] * kb_imod(z, g.size[2]);
+    int c = kb_wrap(x, g.size[0]);
+    if (m.dim >= 2) c += g.size[0] * kb_wrap(y, g.size[1]);
+    if (m.dim >= 3) c += g.size[0] * g.size[1] * kb_wrap(z, g.size[2]);
     return c;
 }
 
