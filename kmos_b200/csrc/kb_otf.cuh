@@ -48,6 +48,7 @@ struct KbOtfParams {
     KbScalars* sc;
     double *rates_matrix, *accum_proc, *lut;
     long long nsteps;
+    const int32_t* lanes = nullptr;  // kb_otf_fast.cuh: the model's otf lane tables (devtables.compile_otf_tables)
 };
 
 template <typename idx_t>

@@ -75,6 +75,96 @@ __device__ __forceinline__ int kb_otff_search(const double* a, int m, double val
     return k;
 }
 
+// The first error any lane ran into becomes lane 0's (the lane whose status is stored): lanes execute statements
+// in textual order, so the lowest lane is the reference's first.
+template <typename idx_t>
+__device__ __forceinline__ void kb_otff_merge_status(KbReplica<idx_t>& r, int lane) {
+    const unsigned bad = __ballot_sync(KB_FULL, r.status != KB_OK);
+    if (!bad) return;
+    const int src = __ffs(bad) - 1;
+    const int st = __shfl_sync(KB_FULL, r.status, src);
+    int e[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) e[i] = __shfl_sync(KB_FULL, r.err[i], src);
+    if (lane == 0 && src != 0) {
+        r.status = st;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) r.err[i] = e[i];
+    }
+}
+
+// run_proc_<proc>(cell) with the statements of its first three blocks spread over the lanes (layout and
+// rationale: devtables.py, compile_otf_tables).  Statements on one process keep their textual order (rank among
+// the lanes that name it); statements on different processes touch different rows of avail_sites and
+// rates_matrix.  Bit-identical to lane 0 interpreting the routine.
+template <typename idx_t>
+__device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx_t>& r, const KbModelView& m,
+                                              const KbGeom& g, const int32_t* T, int proc, int cell, int lane) {
+    const int32_t* ev = T + T[3] + 8 * (proc - 1);
+    const int32_t* ops = T + T[4];
+    int base[4];
+    it.cell_coords(cell, base);
+    base[3] = 0;  // the routine is called on the cell: site types are the statements' own fourth offsets
+    if (lane == 0) r.procstat[proc - 1]++;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // -- if (can_do(q, site)) del_proc(q, site)
+    for (int b0 = 0; b0 < ev[1]; b0 += 32) {
+        const bool on = b0 + lane < ev[1];
+        const int32_t* op = ops + 10 * (ev[0] + b0 + (on ? lane : 0));
+        const int q = op[0];
+        const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
+        const bool fire = on && it.pos_of(q, s.cell, s.n) != 0;  // every lane's guard in one DRAM round trip
+        const unsigned peers = __match_any_sync(KB_FULL, fire ? q : -1 - lane);
+        const int rank = __popc(peers & lt_mask);
+        const int maxrank = __reduce_max_sync(KB_FULL, fire ? rank : 0);
+        for (int k = 0; k <= maxrank; ++k) {
+            // re-checked at its turn: an earlier del of the same process may have been on the same site
+            if (fire && rank == k && it.pos_of(q, s.cell, s.n)) it.del_proc(q, s.cell, s.n);
+            __syncwarp();
+        }
+    }
+    // -- replace_species(site, old, new)
+    for (int b0 = 0; b0 < ev[3]; b0 += 32) {
+        if (b0 + lane < ev[3]) {
+            const int32_t* op = ops + 10 * (ev[2] + b0 + lane);
+            const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
+            it.replace_species(s.cell, s.n, op[0], op[5]);
+        }
+    }
+    __syncwarp();
+    // -- if (can_do(q, site)) update_rates_matrix(q, site, gr_q(cell'))
+    for (int b0 = 0; b0 < ev[5]; b0 += 32) {
+        const bool on = b0 + lane < ev[5];
+        const int32_t* op = ops + 10 * (ev[4] + b0 + (on ? lane : 0));
+        const int q = op[0];
+        const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
+        const int pos = on ? it.pos_of(q, s.cell, s.n) : 0;
+        const bool fire = pos != 0;
+        double rate = 0.0, old = 0.0;
+        double* rm = r.rates_matrix + (size_t)(q - 1) * (g.ncells + 1);
+        if (fire) {
+            old = rm[pos - 1];
+            rate = it.eval_gr(op[5], base, op + 6);
+            rm[pos - 1] = rate;
+        }
+        // block sum and row total of one process: in textual order, like update_rates_matrix one by one
+        const unsigned peers = __match_any_sync(KB_FULL, fire ? q : -1 - lane);
+        const int rank = __popc(peers & lt_mask);
+        const int maxrank = __reduce_max_sync(KB_FULL, fire ? rank : 0);
+        for (int k = 0; k <= maxrank; ++k) {
+            if (fire && rank == k) {
+                if (r.blk) r.blk[(size_t)(q - 1) * r.blk_n + ((pos - 1) >> 8)] += rate - old;
+                rm[g.ncells] = KB_SUB(KB_ADD(rm[g.ncells], rate), old);
+            }
+            __syncwarp();
+        }
+    }
+    kb_otff_merge_status(r, lane);
+    // -- add_proc(q, site, gr_q(cell')) and the select case nests around them: byte-code, lane 0
+    if (lane == 0 && ev[6] >= 0 && r.status != KB_BAD_MODEL) it.exec(ev[6], base);
+    __syncwarp();
+}
+
 template <typename idx_t>
 __global__ void __launch_bounds__(32 * KB_OTFF_WARPS) kb_otf_fast_kernel(const KbOtfParams prm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -184,11 +274,16 @@ __global__ void __launch_bounds__(32 * KB_OTFF_WARPS) kb_otf_fast_kernel(const K
             if (lane == 0) while (k > 0 && !(rm[k] > 0.)) --k;
             k = __shfl_sync(KB_FULL, k, 0);
         }
-        if (lane == 0) {
-            const int cell = (int)r.p1[(size_t)(p - 1) * C + k];
-            it.run_proc_nr(p, cell);
+        if (prm.lanes) {
+            const int cell = (int)r.p1[(size_t)(p - 1) * C + k];  // one address for the whole warp
+            kb_otff_event(it, r, prm.m, prm.g, prm.lanes, p, cell, lane);
+        } else {
+            if (lane == 0) {
+                const int cell = (int)r.p1[(size_t)(p - 1) * C + k];
+                it.run_proc_nr(p, cell);
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     if (lane == 0) {
         KbScalars s = s0;

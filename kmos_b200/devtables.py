@@ -609,6 +609,99 @@ def compile_latint_tables(ir):
 
 
 # ======================================================================================================
+# otf: lane tables for the production kernel (kb_otf_fast.cuh)
+# ======================================================================================================
+#
+# run_proc_<proc>(cell) of the otf generator (kmos/io/__init__.py:3328-3596) has a fixed shape:
+#     if (can_do(q, cell + o)) del_proc(q, cell + o)                                   disabled processes
+#     replace_species(...)                                                             the actions
+#     if (can_do(q, cell + o)) update_rates_matrix(q, cell + o, gr_q(cell + o'))       changed bystanders
+#     add_proc(q, cell + o, gr_q(cell + o')) / select case nests of them               enabled processes
+# Executed by one lane every statement is a chain of dependent DRAM accesses.  The first three blocks go to
+# the lanes of the warp, one statement per lane (statements on one process keep their textual order, as in
+# the lat_int kernel); the last block stays byte-code -- a routine of its own, run by lane 0.
+#
+# Section layout (int32 words, offsets relative to the section start):
+#     [0] version=5 [1] supported [2] n_events [3] events_off [4] ops_off [5] n_ops [6..15] reserved
+#     events  8 words per process: dels_start, n_dels, writes_start, n_writes, upds_start, n_upds,
+#             tail routine id (-1: none), 0
+#     ops     10 words: del     q, dx, dy, dz, n, 0...
+#                       write   old, dx, dy, dz, n, new, 0...
+#                       update  q, dx, dy, dz, n, gr id, gx, gy, gz, gn       (gr evaluated on cell + g)
+OTF_VERSION = 5
+OTF_OP_WORDS = 10
+
+
+def compile_otf_tables(ir, asm):
+    """Lane tables of an otf model; assembles one tail routine per distinct run_proc routine into `asm`."""
+    info = {"supported": False}
+    header = [OTF_VERSION, 0] + [0] * (HEADER_WORDS - 2)
+    nproc = len(ir["procs"])
+
+    def only_adds(block):
+        for st in block:
+            if st[0] == "select":
+                if not all(only_adds(body) for _k, body in st[2]):
+                    return False
+            elif not (st[0] == "add" and not isinstance(st[1], list) and st[3] is not None):
+                return False
+        return True
+
+    try:
+        ops, events, cache = [], [], {}
+        for p in range(nproc):
+            calls = ir["run_proc"][p]
+            if len(calls) != 1 or calls[0][0] != "call" or calls[0][2] != [0, 0, 0, -1]:
+                raise Unsupported("run_proc_nr of process %d is not a single cell routine" % (p + 1))
+            rname = calls[0][1]
+            if rname not in cache:
+                dels, writes, upds = [], [], []
+                stmts = list(ir["routines"][rname])
+                i = 0
+                while i < len(stmts) and stmts[i][0] == "if_can" and len(stmts[i][3]) == 1 and stmts[i][3][0][0] == "del":
+                    st, d = stmts[i], stmts[i][3][0]
+                    if isinstance(d[1], list) or d[1] != st[1] or d[2] != st[2]:
+                        raise Unsupported("guarded del of another process or site")
+                    dels.append([st[1]] + st[2] + [0] * 5)
+                    i += 1
+                while i < len(stmts) and stmts[i][0] == "replace":
+                    st = stmts[i]
+                    writes.append([st[2]] + st[1] + [st[3]] + [0] * 4)
+                    i += 1
+                while i < len(stmts) and stmts[i][0] == "if_can" and len(stmts[i][3]) == 1 and \
+                        stmts[i][3][0][0] == "update_rate":
+                    st, u = stmts[i], stmts[i][3][0]
+                    if u[1] != st[1] or u[2] != st[2] or u[3][0] != "gr":
+                        raise Unsupported("guarded update of another process or site")
+                    upds.append([st[1]] + st[2] + [asm.gr_id(u[3][1])] + u[3][2])
+                    i += 1
+                tail = stmts[i:]
+                if not only_adds(tail):
+                    raise Unsupported("%s: statements after the update block other than add_proc" % rname)
+                if len(dels) > 255 or len(upds) > 255 or len(writes) > 32:
+                    raise Unsupported("%s: too many statements" % rname)
+                tail_id = asm.anon_routine("__otf_tail_" + rname, tail) if tail else -1
+                ev = [len(ops), len(dels)]
+                ops += dels
+                ev += [len(ops), len(writes)]
+                ops += writes
+                ev += [len(ops), len(upds), tail_id, 0]
+                ops += upds
+                cache[rname] = ev
+            events += cache[rname]
+    except Unsupported as e:
+        info["reason"] = str(e)
+        return header, info
+    events_off = HEADER_WORDS
+    ops_off = events_off + len(events)
+    header = [OTF_VERSION, 1, nproc, events_off, ops_off, len(ops)] + [0] * (HEADER_WORDS - 6)
+    words = header + events + [w for op in ops for w in op]
+    assert all(len(op) == OTF_OP_WORDS for op in ops)
+    info.update({"supported": True, "n_ops": len(ops), "bytes": 4 * len(words)})
+    return words, info
+
+
+# ======================================================================================================
 # local_smart on lattices that do not fit shared memory: tables for the warp-per-replica HBM kernel
 # ======================================================================================================
 #

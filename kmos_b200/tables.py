@@ -246,6 +246,11 @@ def build_blob(ir, with_device=True):
                              "size": size}
             lut_total += size
 
+    otf_dev = None
+    if with_device and ir["backend"] == "otf":   # assembles the events' tail routines: before the code is laid out
+        from . import devtables
+        otf_dev = devtables.compile_otf_tables(ir, asm)
+
     code = []
     routines = []
     for words in asm.routine_code:
@@ -264,7 +269,7 @@ def build_blob(ir, with_device=True):
             "n_routines": len(asm.routine_code)}
     if with_device:
         from . import devtables
-        dev_words, dev_info = devtables.compile_device_tables(ir, asm)
+        dev_words, dev_info = otf_dev if otf_dev is not None else devtables.compile_device_tables(ir, asm)
         sections.append((SEC_DEVICE, dev_words))
         info["device"] = dev_info
         if ir["backend"] == "local_smart":

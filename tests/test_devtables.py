@@ -213,3 +213,46 @@ def test_two_replace_species_calls_on_one_site_become_one_write():
         if name.startswith("AB_reaction"):
             assert [(old, new) for _s, old, new in writes] == [(A, B)], (name, writes)
             assert len(ops) > 0
+
+
+@pytest.mark.parametrize("name", ["pairwise_otf_otf", "intzgb_otf", "ruo2default_otf", "multidentate_otf", "hop3d_otf",
+                                  "ab_otf", "mini_101_otf"])
+def test_otf_lane_tables_partition_every_event_routine(name):
+    """compile_otf_tables: every statement of run_proc_<proc> ends up in exactly one of the del / write / update
+    blocks or in the tail routine, in order, with the operands of the statement."""
+    from kmos_b200 import tables
+    ir, _blob, info = load_model(name)
+    assert info["device"]["supported"], info["device"].get("reason")
+    blob, info2 = tables.build_blob(ir)
+    words = None
+    n_sections = int(blob[13])
+    for i in range(n_sections):
+        sid, off, ln = (int(v) for v in blob[14 + 3 * i:17 + 3 * i])
+        if sid == tables.SEC_DEVICE:
+            words = [int(w) for w in blob[off:off + ln]]
+    assert words is not None and words[0] == dt.OTF_VERSION and words[1] == 1 and words[2] == len(ir["procs"])
+    gr_by_id = {}
+    for st_name, g in info2["gr"].items():
+        gr_by_id[st_name] = g
+    for p in range(len(ir["procs"])):
+        ev = words[words[3] + 8 * p: words[3] + 8 * p + 8]
+        stmts = ir["routines"][ir["run_proc"][p][0][1]]
+        ops = lambda start, n: [words[words[4] + 10 * (start + i): words[4] + 10 * (start + i) + 10] for i in range(n)]
+        dels, writes, upds = ops(ev[0], ev[1]), ops(ev[2], ev[3]), ops(ev[4], ev[5])
+        k = 0
+        for op in dels:
+            assert stmts[k][0] == "if_can" and [stmts[k][1]] + stmts[k][2] == op[:5] and stmts[k][3][0][0] == "del"
+            k += 1
+        for op in writes:
+            assert stmts[k][0] == "replace" and [stmts[k][2]] + stmts[k][1] + [stmts[k][3]] == op[:6]
+            k += 1
+        for op in upds:
+            u = stmts[k][3][0]
+            assert stmts[k][0] == "if_can" and u[0] == "update_rate" and [stmts[k][1]] + stmts[k][2] == op[:5]
+            assert op[6:10] == u[3][2]
+            k += 1
+        tail = stmts[k:]
+        assert (ev[6] >= 0) == bool(tail)
+        assert all(st[0] in ("add", "select") for st in tail)
+        if tail:
+            assert info2["routine_ids"]["__otf_tail_" + ir["run_proc"][p][0][1]] == ev[6]

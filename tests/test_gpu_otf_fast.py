@@ -20,10 +20,18 @@ pytestmark = pytest.mark.gpu
     ("pairwise_otf_otf", [64, 48], [2100, 900]),         # 12 blocks per row, crosses a re-accumulation (2048)
     ("intzgb_otf", [20, 18], [1500, 1500]),
     ("ruo2default_otf", [20, 20], [1200, 1200]),         # 36 processes, 2 sites per cell
+    ("multidentate_otf", [20, 18], [1500, 1500]),        # species spanning two and four sites
+    ("hop3d_otf", [8, 7, 6], [1500, 1500]),              # z offsets
+    ("ab_otf", [20, 20], [1500, 1500]),
 ])
-def test_fast_selection_walks_the_exact_trajectory(name, size, chunks):
+@pytest.mark.parametrize("lanes", ["lanes", "lane0"])
+def test_fast_selection_walks_the_exact_trajectory(name, size, chunks, lanes, monkeypatch):
+    """lanes: the event's guarded dels, lattice writes and guarded rate updates spread over the warp
+    (devtables.compile_otf_tables); lane0: the whole routine interpreted by lane 0."""
     from kmos_b200 import engine
+    monkeypatch.setenv("KMOS_B200_OTF_LANES", "1" if lanes == "lanes" else "0")
     ir, blob, info = load_model(name)
+    assert info["device"]["supported"], info["device"].get("reason")
     R = 5
     rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + 3)
     b = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=rates, lut=lut,
