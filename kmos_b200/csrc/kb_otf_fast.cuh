@@ -107,6 +107,20 @@ __device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx
     base[3] = 0;  // the routine is called on the cell: site types are the statements' own fourth offsets
     if (lane == 0) r.procstat[proc - 1]++;
     const unsigned lt_mask = (1u << lane) - 1u;
+    // Loads nobody waits for until the end of the event: the back-pointers the update block will test and the
+    // lattice rows its gr_<proc> functions count bystanders in are on their way while the dels run (the
+    // statements load them again at their proper time -- from L1).  Values: at most 2^17 resp. 255.
+    uint32_t warm = 0;
+    if (lane < ev[5] && lane < 24) {
+        const int32_t* op = ops + 10 * (ev[4] + lane);
+        const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
+        warm = (uint32_t)r.p2[(size_t)(op[0] - 1) * g.ncells + s.cell];
+    } else if (lane >= 24 && lane < 31) {
+        const int j = lane - 24;  // rows y-2 .. y+2 of the lattice, planes z-1, z+1
+        const int32_t off[4] = {0, (j < 5 && m.dim >= 2) ? j - 2 : 0, (j >= 5 && m.dim >= 3) ? 2 * j - 11 : 0, 1};
+        const typename KbInterp<idx_t>::Site s = it.site_of(base, off);
+        warm = r.lattice[s.cell * m.spuck];
+    }
     // -- if (can_do(q, site)) del_proc(q, site)
     for (int b0 = 0; b0 < ev[1]; b0 += 32) {
         const bool on = b0 + lane < ev[1];
@@ -159,6 +173,7 @@ __device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx
             __syncwarp();
         }
     }
+    if (warm >= 0x40000000u) r.status = KB_BAD_MODEL;  // never: ends the life of the warm-up loads
     kb_otff_merge_status(r, lane);
     // -- add_proc(q, site, gr_q(cell')) and the select case nests around them: byte-code, lane 0
     if (lane == 0 && ev[6] >= 0 && r.status != KB_BAD_MODEL) it.exec(ev[6], base);
@@ -193,6 +208,7 @@ __global__ void __launch_bounds__(32 * KB_OTFF_WARPS) kb_otf_fast_kernel(const K
     r.seed = s0.seed; r.replica = s0.replica; r.status = s0.status;
     for (int i = 0; i < 5; ++i) r.err[i] = s0.err[i];
     KbInterp<idx_t> it(prm.m, prm.g, r);
+    __shared__ double s_accum[KB_OTFF_WARPS][64];  // accum_rates of each warp's replica (P <= 64)
 
     for (long long step = 0; step < prm.nsteps; ++step) {
         if (__shfl_sync(KB_FULL, r.status, 0) != KB_OK) break;
@@ -221,40 +237,54 @@ __global__ void __launch_bounds__(32 * KB_OTFF_WARPS) kb_otf_fast_kernel(const K
             }
             __syncwarp();
         }
-        // -- update_accum_rate over the maintained row totals, update_clocks, process search (lane 0)
-        int p = 0, n = 0;
-        double value = 0.0;
+        // -- update_accum_rate over the maintained row totals, update_clocks, update_integ_rate, process search.
+        // Lane l holds the rows l and l + 32: one round trip for all totals, counters and integrals instead of
+        // one per process; the accumulation itself is the reference's serial recurrence, repeated by every lane
+        // on shuffled values (same operations in the same order: same bits), the search reads it from shared memory.
+        const bool h0 = lane < P, h1 = lane + 32 < P;
+        const double tot0 = h0 ? r.rates_matrix[(size_t)lane * (C + 1) + C] : 0.0;
+        const double tot1 = h1 ? r.rates_matrix[(size_t)(lane + 32) * (C + 1) + C] : 0.0;
+        const int ns0 = h0 ? r.nsites[lane] : 0, ns1 = h1 ? r.nsites[lane + 32] : 0;
+        const double in0 = h0 ? r.integ[lane] : 0.0, in1 = h1 ? r.integ[lane + 32] : 0.0;
+        double* sacc = s_accum[warp];
+        double acc = 0.0;
+        for (int i = 0; i < P; ++i) {
+            const double t = __shfl_sync(KB_FULL, i < 32 ? tot0 : tot1, i & 31);
+            acc = (i == 0) ? t : acc + t;
+            if ((i & 31) == lane) sacc[i] = acc;
+        }
+        __syncwarp();
+        const double total = acc;  // accum_rates(nr_of_proc)
+        if (h0) r.accum[lane] = sacc[lane];
+        if (h1) r.accum[lane + 32] = sacc[lane + 32];
+        int p = 0;
+        double ran_site = 0.0;
+        bool alive = total > 0.;
         if (lane == 0) {
-            double acc = 0.0;
-            for (int i = 0; i < P; ++i) {
-                const double tot = r.rates_matrix[(size_t)i * (C + 1) + C];
-                acc = (i == 0) ? tot : acc + tot;
-                r.accum[i] = acc;
-            }
-            const double total = r.accum[P - 1];
-            if (!(total > 0.)) {
+            if (!alive) {
                 it.fail(KB_DEADLOCK);
             } else {
-                double ran_time, ran_proc, ran_site;
+                double ran_time, ran_proc;
                 kb_philox_step(r.seed, r.replica, (uint64_t)r.kmc_step, &ran_time, &ran_proc, &ran_site);
                 r.kmc_time_step = -log(ran_time) / total;
                 r.kmc_time = r.kmc_time + r.kmc_time_step;
                 r.kmc_step = r.kmc_step + 1;
-                it.update_integ_rate();
-                p = KbInterp<idx_t>::interval_search_real(r.accum, P, ran_proc * total);
-                if (p == 0 || r.nsites[p - 1] <= 0) {
-                    it.fail(KB_DEADLOCK);
-                    p = 0;
-                } else {
-                    n = r.nsites[p - 1];
-                    value = ran_site * r.rates_matrix[(size_t)(p - 1) * (C + 1) + C];
-                }
+                p = KbInterp<idx_t>::interval_search_real(sacc, P, ran_proc * total);
             }
         }
+        if (!alive) continue;  // stopped: the status check at the top of the loop ends the launch for this replica
+        const double dt = __shfl_sync(KB_FULL, r.kmc_time_step, 0);
+        if (h0) r.integ[lane] = KB_ADD(in0, KB_MUL(tot0, dt));
+        if (h1) r.integ[lane + 32] = KB_ADD(in1, KB_MUL(tot1, dt));
         p = __shfl_sync(KB_FULL, p, 0);
-        if (p == 0) continue;  // stopped: the status check at the top of the loop ends the launch for this replica
-        n = __shfl_sync(KB_FULL, n, 0);
-        value = __shfl_sync(KB_FULL, value, 0);
+        const int psel = p > 0 ? p - 1 : 0;
+        const int n = __shfl_sync(KB_FULL, psel < 32 ? ns0 : ns1, psel & 31);
+        const double tsel = __shfl_sync(KB_FULL, psel < 32 ? tot0 : tot1, psel & 31);
+        if (p == 0 || n <= 0) {
+            if (lane == 0) it.fail(KB_DEADLOCK);
+            continue;
+        }
+        const double value = __shfl_sync(KB_FULL, ran_site * tsel, 0);
         // -- determine_procsite: block, then position inside the block
         const double* rm = r.rates_matrix + (size_t)(p - 1) * (C + 1);
         const int nb = (n + KB_OTFF_BLOCK - 1) >> KB_OTFF_SHIFT;
