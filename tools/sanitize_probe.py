@@ -15,6 +15,8 @@ from kmos_b200 import capi, engine  # noqa: E402
 CASES = [("ruo2_local_smart", [9, 7], capi.KERNEL_GENERATED), ("zgb_local_smart", [12, 11], capi.KERNEL_GENERATED),
          ("mini_101_local_smart", [6, 5], capi.KERNEL_GENERATED), ("pairwise_local_smart", [10, 9], capi.KERNEL_GENERATED),
          ("pairwise_otf_otf", [24, 20], capi.KERNEL_OTF_FAST), ("intzgb_otf", [20, 18], capi.KERNEL_OTF_FAST),
+         ("ruo2default_otf", [20, 20], capi.KERNEL_OTF_FAST), ("hop3d_otf", [8, 7, 6], capi.KERNEL_OTF_FAST),
+         ("multidentate_otf", [20, 18], capi.KERNEL_OTF_FAST),
          ("ruo2_local_smart", [9, 7], capi.KERNEL_SMEM), ("zgb_local_smart", [30, 30], capi.KERNEL_SMEM),
          ("ruo2_local_smart", [9, 7], capi.KERNEL_WARP_HBM), ("pairwise_lat_int", [9, 8], capi.KERNEL_WARP_HBM),
          ("pairwise84_lat_int", [9, 8], capi.KERNEL_WARP_HBM), ("pdopd_local_smart", [6, 5], capi.KERNEL_WARP_HBM),
