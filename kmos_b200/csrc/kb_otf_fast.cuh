@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(32 * KB_OTFF_WARPS) kb_otf_fast_kernel(const K
         }
         if (!alive) continue;  // stopped: the status check at the top of the loop ends the launch for this replica
         const double dt = __shfl_sync(KB_FULL, r.kmc_time_step, 0);
+        r.kmc_step = __shfl_sync(KB_FULL, (long long)r.kmc_step, 0);  // every lane may have to report an error
         if (h0) r.integ[lane] = KB_ADD(in0, KB_MUL(tot0, dt));
         if (h1) r.integ[lane + 32] = KB_ADD(in1, KB_MUL(tot1, dt));
         p = __shfl_sync(KB_FULL, p, 0);
