@@ -174,6 +174,22 @@ __device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx
         }
     }
     if (warm >= 0x40000000u) r.status = KB_BAD_MODEL;  // never: ends the life of the warm-up loads
+    // -- add_proc(q, site, gr_q(cell')) where the enabled processes are a plain list: all rates at once, lists
+    // of one process in textual order
+    if (ev[7] > 0) {
+        const bool on = lane < ev[7];
+        const int32_t* op = ops + 10 * (ev[4] + ev[5] + (on ? lane : 0));
+        const int q = op[0];
+        const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
+        const double rate = on ? it.eval_gr(op[5], base, op + 6) : 0.0;
+        const unsigned peers = __match_any_sync(KB_FULL, on ? q : -1 - lane);
+        const int rank = __popc(peers & lt_mask);
+        const int maxrank = __reduce_max_sync(KB_FULL, on ? rank : 0);
+        for (int k = 0; k <= maxrank; ++k) {
+            if (on && rank == k) it.add_proc(q, s.cell, s.n, rate);
+            __syncwarp();
+        }
+    }
     kb_otff_merge_status(r, lane);
     // -- add_proc(q, site, gr_q(cell')) and the select case nests around them: byte-code, lane 0
     if (lane == 0 && ev[6] >= 0 && r.status != KB_BAD_MODEL) it.exec(ev[6], base);

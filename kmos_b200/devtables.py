@@ -624,10 +624,12 @@ def compile_latint_tables(ir):
 # Section layout (int32 words, offsets relative to the section start):
 #     [0] version=5 [1] supported [2] n_events [3] events_off [4] ops_off [5] n_ops [6..15] reserved
 #     events  8 words per process: dels_start, n_dels, writes_start, n_writes, upds_start, n_upds,
-#             tail routine id (-1: none), 0
+#             tail routine id (-1: none), n_adds (a tail that is a plain list of add_proc statements is stored
+#             as ops behind the updates instead of as a routine)
 #     ops     10 words: del     q, dx, dy, dz, n, 0...
 #                       write   old, dx, dy, dz, n, new, 0...
 #                       update  q, dx, dy, dz, n, gr id, gx, gy, gz, gn       (gr evaluated on cell + g)
+#                       add     like update
 OTF_VERSION = 5
 OTF_OP_WORDS = 10
 
@@ -680,13 +682,17 @@ def compile_otf_tables(ir, asm):
                     raise Unsupported("%s: statements after the update block other than add_proc" % rname)
                 if len(dels) > 255 or len(upds) > 255 or len(writes) > 32:
                     raise Unsupported("%s: too many statements" % rname)
+                adds = []
+                if tail and all(st[0] == "add" for st in tail) and len(tail) <= 32:
+                    adds = [[st[1]] + st[2] + [asm.gr_id(st[3][1])] + st[3][2] for st in tail]
+                    tail = []
                 tail_id = asm.anon_routine("__otf_tail_" + rname, tail) if tail else -1
                 ev = [len(ops), len(dels)]
                 ops += dels
                 ev += [len(ops), len(writes)]
                 ops += writes
-                ev += [len(ops), len(upds), tail_id, 0]
-                ops += upds
+                ev += [len(ops), len(upds), tail_id, len(adds)]
+                ops += upds + adds
                 cache[rname] = ev
             events += cache[rname]
     except Unsupported as e:

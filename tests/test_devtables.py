@@ -252,7 +252,12 @@ def test_otf_lane_tables_partition_every_event_routine(name):
             assert op[6:10] == u[3][2]
             k += 1
         tail = stmts[k:]
-        assert (ev[6] >= 0) == bool(tail)
         assert all(st[0] in ("add", "select") for st in tail)
-        if tail:
-            assert info2["routine_ids"]["__otf_tail_" + ir["run_proc"][p][0][1]] == ev[6]
+        if ev[7]:   # a plain list of add_proc statements: ops behind the updates
+            assert ev[6] == -1 and ev[7] == len(tail)
+            for op, st in zip(ops(ev[4] + ev[5], ev[7]), tail):
+                assert st[0] == "add" and [st[1]] + st[2] == op[:5] and op[6:10] == st[3][2]
+        else:
+            assert (ev[6] >= 0) == bool(tail)
+            if tail:
+                assert info2["routine_ids"]["__otf_tail_" + ir["run_proc"][p][0][1]] == ev[6]
