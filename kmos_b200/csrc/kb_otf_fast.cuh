@@ -33,6 +33,7 @@
 #define KB_OTFF_BLOCK (1 << KB_OTFF_SHIFT)
 #define KB_OTFF_REBUILD 2048
 #define KB_OTFF_WARPS 8
+#define KB_OTFF_OP 12  // words per lane-table op (devtables.py, OTF_OP_WORDS)
 
 // first index k in a[0, m) whose inclusive prefix sum exceeds `value` (lane l owns the contiguous chunk
 // [l*per, (l+1)*per), per <= 8), -1 if none; *before = prefix sum in front of k.  Warp-collective.
@@ -112,7 +113,7 @@ __device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx
     // statements load them again at their proper time -- from L1).  Values: at most 2^17 resp. 255.
     uint32_t warm = 0;
     if (lane < ev[5] && lane < 24) {
-        const int32_t* op = ops + 10 * (ev[4] + lane);
+        const int32_t* op = ops + KB_OTFF_OP * (ev[4] + lane);
         const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
         warm = (uint32_t)r.p2[(size_t)(op[0] - 1) * g.ncells + s.cell];
     } else if (lane >= 24 && lane < 31) {
@@ -124,7 +125,7 @@ __device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx
     // -- if (can_do(q, site)) del_proc(q, site)
     for (int b0 = 0; b0 < ev[1]; b0 += 32) {
         const bool on = b0 + lane < ev[1];
-        const int32_t* op = ops + 10 * (ev[0] + b0 + (on ? lane : 0));
+        const int32_t* op = ops + KB_OTFF_OP * (ev[0] + b0 + (on ? lane : 0));
         const int q = op[0];
         const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
         const bool fire = on && it.pos_of(q, s.cell, s.n) != 0;  // every lane's guard in one DRAM round trip
@@ -140,7 +141,7 @@ __device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx
     // -- replace_species(site, old, new)
     for (int b0 = 0; b0 < ev[3]; b0 += 32) {
         if (b0 + lane < ev[3]) {
-            const int32_t* op = ops + 10 * (ev[2] + b0 + lane);
+            const int32_t* op = ops + KB_OTFF_OP * (ev[2] + b0 + lane);
             const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
             it.replace_species(s.cell, s.n, op[0], op[5]);
         }
@@ -149,7 +150,7 @@ __device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx
     // -- if (can_do(q, site)) update_rates_matrix(q, site, gr_q(cell'))
     for (int b0 = 0; b0 < ev[5]; b0 += 32) {
         const bool on = b0 + lane < ev[5];
-        const int32_t* op = ops + 10 * (ev[4] + b0 + (on ? lane : 0));
+        const int32_t* op = ops + KB_OTFF_OP * (ev[4] + b0 + (on ? lane : 0));
         const int q = op[0];
         const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
         const int pos = on ? it.pos_of(q, s.cell, s.n) : 0;
@@ -174,19 +175,26 @@ __device__ __forceinline__ void kb_otff_event(KbInterp<idx_t>& it, KbReplica<idx
         }
     }
     if (warm >= 0x40000000u) r.status = KB_BAD_MODEL;  // never: ends the life of the warm-up loads
-    // -- add_proc(q, site, gr_q(cell')) where the enabled processes are a plain list: all rates at once, lists
-    // of one process in textual order
-    if (ev[7] > 0) {
-        const bool on = lane < ev[7];
-        const int32_t* op = ops + 10 * (ev[4] + ev[5] + (on ? lane : 0));
+    // -- the if-tree of add_proc(q, site, gr_q(cell')) statements, flattened: each statement with the case labels
+    // on its path as conditions; all conditions and rates at once, the appends of one process in textual order
+    const int32_t* conds = T + T[6];
+    for (int b0 = 0; b0 < ev[7]; b0 += 32) {
+        const bool on = b0 + lane < ev[7];
+        const int32_t* op = ops + KB_OTFF_OP * (ev[4] + ev[5] + b0 + (on ? lane : 0));
         const int q = op[0];
+        bool fire = on;
+        for (int c = 0; c < op[11] && fire; ++c) {
+            const int32_t* cd = conds + 5 * (op[10] + c);
+            const int sp = it.species_at(base, cd);
+            fire = ((uint32_t)cd[4] >> (sp >= 0 ? sp : 31)) & 1u;
+        }
         const typename KbInterp<idx_t>::Site s = it.site_of(base, op + 1);
-        const double rate = on ? it.eval_gr(op[5], base, op + 6) : 0.0;
-        const unsigned peers = __match_any_sync(KB_FULL, on ? q : -1 - lane);
+        const double rate = fire ? it.eval_gr(op[5], base, op + 6) : 0.0;
+        const unsigned peers = __match_any_sync(KB_FULL, fire ? q : -1 - lane);
         const int rank = __popc(peers & lt_mask);
-        const int maxrank = __reduce_max_sync(KB_FULL, on ? rank : 0);
+        const int maxrank = __reduce_max_sync(KB_FULL, fire ? rank : 0);
         for (int k = 0; k <= maxrank; ++k) {
-            if (on && rank == k) it.add_proc(q, s.cell, s.n, rate);
+            if (fire && rank == k) it.add_proc(q, s.cell, s.n, rate);
             __syncwarp();
         }
     }

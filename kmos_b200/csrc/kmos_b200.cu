@@ -1091,7 +1091,7 @@ extern "C" int kmos_b200_do_kmc_steps(kmos_b200_batch* b, int64_t n) {
             // version 5, devtables.compile_otf_tables); KMOS_B200_OTF_LANES=0 keeps lane 0 interpreting
             const char* le = getenv("KMOS_B200_OTF_LANES");
             const kmos_b200_model* mm = b->model;
-            if (!(le && le[0] == '0') && mm->h.dev && mm->h.dev_len >= 16 && mm->h.dev[0] == 5 && mm->h.dev[1] == 1)
+            if (!(le && le[0] == '0') && mm->h.dev && mm->h.dev_len >= 16 && mm->h.dev[0] == 6 && mm->h.dev[1] == 1)
                 op.lanes = b->d.dev;
             if (b->idx32) kb_otf_fast_kernel<uint32_t><<<fblocks, 32 * KB_OTFF_WARPS, 0, b->stream>>>(op);
             else kb_otf_fast_kernel<uint16_t><<<fblocks, 32 * KB_OTFF_WARPS, 0, b->stream>>>(op);

@@ -42,6 +42,8 @@ Section layout (int32 words, offsets relative to the section start):
     offsets  1 word each: (dx&255) | (dy&255)<<8 | (dz&255)<<16
     procinfo 1 word per process: arena | dir<<6 | cls<<7 | member<<12 | anchor_n<<15
 """
+import os
+
 EVENT_WORDS = 8
 MAX_ROUNDS = 8
 MAX_WRITES = 4
@@ -622,16 +624,21 @@ def compile_latint_tables(ir):
 # the lat_int kernel); the last block stays byte-code -- a routine of its own, run by lane 0.
 #
 # Section layout (int32 words, offsets relative to the section start):
-#     [0] version=5 [1] supported [2] n_events [3] events_off [4] ops_off [5] n_ops [6..15] reserved
+#     [0] version=6 [1] supported [2] n_events [3] events_off [4] ops_off [5] n_ops [6] conds_off [7] n_conds
 #     events  8 words per process: dels_start, n_dels, writes_start, n_writes, upds_start, n_upds,
-#             tail routine id (-1: none), n_adds (a tail that is a plain list of add_proc statements is stored
-#             as ops behind the updates instead of as a routine)
-#     ops     10 words: del     q, dx, dy, dz, n, 0...
+#             tail routine id (-1: none), n_adds (ops behind the updates)
+#     ops     12 words: del     q, dx, dy, dz, n, 0...
 #                       write   old, dx, dy, dz, n, new, 0...
-#                       update  q, dx, dy, dz, n, gr id, gx, gy, gz, gn       (gr evaluated on cell + g)
-#                       add     like update
-OTF_VERSION = 5
-OTF_OP_WORDS = 10
+#                       update  q, dx, dy, dz, n, gr id, gx, gy, gz, gn, 0, 0     (gr evaluated on cell + g)
+#                       add     q, dx, dy, dz, n, gr id, gx, gy, gz, gn, conds_start, n_conds
+#     conds   5 words: dx, dy, dz, n, species mask (bit 31: the null species passes)
+# The add block is the generator's if-tree (select case nests, io/__init__.py:2568-2655) flattened: every
+# add_proc statement with the case labels on its path as conditions, in textual order.  The lattice does not
+# change while the block runs and exactly one case of a select is taken, so the flattened list appends the same
+# processes in the same order.  Blocks with more than 255 statements or 8 conditions stay a byte-code routine.
+OTF_VERSION = 6
+OTF_OP_WORDS = 12
+OTF_MAX_CONDS = 8
 
 
 def compile_otf_tables(ir, asm):
@@ -649,8 +656,31 @@ def compile_otf_tables(ir, asm):
                 return False
         return True
 
+    n_species = len(ir["species"])
+
+    def flatten_adds(block, path, out):
+        for st in block:
+            if st[0] == "add":
+                out.append((st, list(path)))
+            else:  # select: first matching label wins, `case default` takes what no label names (and null)
+                seen = 0
+                default_body = None
+                for key, body in st[2]:
+                    if key is None:
+                        default_body = body
+                        continue
+                    mask = 0
+                    for sp in key:
+                        mask |= 1 << sp
+                    mask &= ~seen
+                    seen |= mask
+                    flatten_adds(body, path + [st[1] + [mask]], out)
+                if default_body is not None:
+                    rest = ((1 << n_species) - 1) & ~seen
+                    flatten_adds(default_body, path + [st[1] + [rest | (1 << 31)]], out)
+
     try:
-        ops, events, cache = [], [], {}
+        ops, events, cache, conds = [], [], {}, []
         for p in range(nproc):
             calls = ir["run_proc"][p]
             if len(calls) != 1 or calls[0][0] != "call" or calls[0][2] != [0, 0, 0, -1]:
@@ -664,27 +694,31 @@ def compile_otf_tables(ir, asm):
                     st, d = stmts[i], stmts[i][3][0]
                     if isinstance(d[1], list) or d[1] != st[1] or d[2] != st[2]:
                         raise Unsupported("guarded del of another process or site")
-                    dels.append([st[1]] + st[2] + [0] * 5)
+                    dels.append([st[1]] + st[2] + [0] * 7)
                     i += 1
                 while i < len(stmts) and stmts[i][0] == "replace":
                     st = stmts[i]
-                    writes.append([st[2]] + st[1] + [st[3]] + [0] * 4)
+                    writes.append([st[2]] + st[1] + [st[3]] + [0] * 6)
                     i += 1
                 while i < len(stmts) and stmts[i][0] == "if_can" and len(stmts[i][3]) == 1 and \
                         stmts[i][3][0][0] == "update_rate":
                     st, u = stmts[i], stmts[i][3][0]
                     if u[1] != st[1] or u[2] != st[2] or u[3][0] != "gr":
                         raise Unsupported("guarded update of another process or site")
-                    upds.append([st[1]] + st[2] + [asm.gr_id(u[3][1])] + u[3][2])
+                    upds.append([st[1]] + st[2] + [asm.gr_id(u[3][1])] + u[3][2] + [0, 0])
                     i += 1
                 tail = stmts[i:]
                 if not only_adds(tail):
                     raise Unsupported("%s: statements after the update block other than add_proc" % rname)
                 if len(dels) > 255 or len(upds) > 255 or len(writes) > 32:
                     raise Unsupported("%s: too many statements" % rname)
-                adds = []
-                if tail and all(st[0] == "add" for st in tail) and len(tail) <= 32:
-                    adds = [[st[1]] + st[2] + [asm.gr_id(st[3][1])] + st[3][2] for st in tail]
+                adds, flat = [], []
+                flatten_adds(tail, [], flat)
+                if flat and len(flat) <= 255 and all(len(path) <= OTF_MAX_CONDS for _st, path in flat) and \
+                        os.environ.get("KMOS_B200_OTF_FLATTEN", "1") != "0":   # "0": keep the routine (tests)
+                    for st, path in flat:
+                        adds.append([st[1]] + st[2] + [asm.gr_id(st[3][1])] + st[3][2] + [len(conds), len(path)])
+                        conds += path
                     tail = []
                 tail_id = asm.anon_routine("__otf_tail_" + rname, tail) if tail else -1
                 ev = [len(ops), len(dels)]
@@ -700,11 +734,17 @@ def compile_otf_tables(ir, asm):
         return header, info
     events_off = HEADER_WORDS
     ops_off = events_off + len(events)
-    header = [OTF_VERSION, 1, nproc, events_off, ops_off, len(ops)] + [0] * (HEADER_WORDS - 6)
-    words = header + events + [w for op in ops for w in op]
-    assert all(len(op) == OTF_OP_WORDS for op in ops)
-    info.update({"supported": True, "n_ops": len(ops), "bytes": 4 * len(words)})
-    return words, info
+    conds_off = ops_off + OTF_OP_WORDS * len(ops)
+    header = [OTF_VERSION, 1, nproc, events_off, ops_off, len(ops), conds_off, len(conds)] + [0] * (HEADER_WORDS - 8)
+    assert all(len(op) == OTF_OP_WORDS for op in ops) and all(len(c) == 5 for c in conds)
+    words = header + events + [w for op in ops for w in op] + [w for c in conds for w in c]
+
+    def s32(w):
+        return w - (1 << 32) if w >= (1 << 31) else w
+
+    info.update({"supported": True, "n_ops": len(ops), "n_conds": len(conds), "bytes": 4 * len(words),
+                 "routine_tails": sum(1 for ev in cache.values() if ev[6] >= 0)})
+    return [s32(w) for w in words], info
 
 
 # ======================================================================================================

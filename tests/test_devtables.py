@@ -237,7 +237,8 @@ def test_otf_lane_tables_partition_every_event_routine(name):
     for p in range(len(ir["procs"])):
         ev = words[words[3] + 8 * p: words[3] + 8 * p + 8]
         stmts = ir["routines"][ir["run_proc"][p][0][1]]
-        ops = lambda start, n: [words[words[4] + 10 * (start + i): words[4] + 10 * (start + i) + 10] for i in range(n)]
+        W = dt.OTF_OP_WORDS
+        ops = lambda start, n: [words[words[4] + W * (start + i): words[4] + W * (start + i) + W] for i in range(n)]
         dels, writes, upds = ops(ev[0], ev[1]), ops(ev[2], ev[3]), ops(ev[4], ev[5])
         k = 0
         for op in dels:
@@ -253,10 +254,28 @@ def test_otf_lane_tables_partition_every_event_routine(name):
             k += 1
         tail = stmts[k:]
         assert all(st[0] in ("add", "select") for st in tail)
-        if ev[7]:   # a plain list of add_proc statements: ops behind the updates
-            assert ev[6] == -1 and ev[7] == len(tail)
-            for op, st in zip(ops(ev[4] + ev[5], ev[7]), tail):
-                assert st[0] == "add" and [st[1]] + st[2] == op[:5] and op[6:10] == st[3][2]
+        if ev[7]:   # the if-tree flattened: every add_proc statement with the case labels on its path
+            assert ev[6] == -1
+
+            def leaves(block, path):
+                for st in block:
+                    if st[0] == "add":
+                        yield st, path
+                    else:
+                        for key, body in st[2]:
+                            yield from leaves(body, path + [(st[1], key, st[2])])
+            flat = list(leaves(tail, []))
+            assert ev[7] == len(flat)
+            n_species = len(ir["species"])
+            for op, (st, path) in zip(ops(ev[4] + ev[5], ev[7]), flat):
+                assert [st[1]] + st[2] == op[:5] and op[6:10] == st[3][2] and op[11] == len(path)
+                for c, (site, key, cases) in enumerate(path):
+                    cd = words[words[6] + 5 * (op[10] + c): words[6] + 5 * (op[10] + c) + 5]
+                    assert cd[:4] == site
+                    named = set(s for k, _b in cases if k is not None for s in k)
+                    want = set(key) if key is not None else set(range(n_species)) - named
+                    assert set(s for s in range(n_species) if (cd[4] >> s) & 1) == want
+                    assert bool((cd[4] >> 31) & 1) == (key is None)
         else:
             assert (ev[6] >= 0) == bool(tail)
             if tail:

@@ -24,14 +24,18 @@ pytestmark = pytest.mark.gpu
     ("hop3d_otf", [8, 7, 6], [1500, 1500]),              # z offsets
     ("ab_otf", [20, 20], [1500, 1500]),
 ])
-@pytest.mark.parametrize("lanes", ["lanes", "lane0"])
+@pytest.mark.parametrize("lanes", ["lanes", "lanes_routine_tail", "lane0"])
 def test_fast_selection_walks_the_exact_trajectory(name, size, chunks, lanes, monkeypatch):
-    """lanes: the event's guarded dels, lattice writes and guarded rate updates spread over the warp
-    (devtables.compile_otf_tables); lane0: the whole routine interpreted by lane 0."""
+    """lanes: the event's guarded dels, lattice writes, guarded rate updates and the flattened if-tree of add_proc
+    statements spread over the warp (devtables.compile_otf_tables); lanes_routine_tail: the add block kept as a
+    byte-code routine run by lane 0 (what very large blocks fall back to); lane0: the whole routine interpreted
+    by lane 0."""
     from kmos_b200 import engine
-    monkeypatch.setenv("KMOS_B200_OTF_LANES", "1" if lanes == "lanes" else "0")
+    monkeypatch.setenv("KMOS_B200_OTF_LANES", "0" if lanes == "lane0" else "1")
+    monkeypatch.setenv("KMOS_B200_OTF_FLATTEN", "0" if lanes == "lanes_routine_tail" else "1")
     ir, blob, info = load_model(name)
     assert info["device"]["supported"], info["device"].get("reason")
+    assert (info["device"]["routine_tails"] > 0) == (lanes == "lanes_routine_tail")
     R = 5
     rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + 3)
     b = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, size, seeds=seeds, rates=rates, lut=lut,

@@ -16,10 +16,10 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 3552
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 size = [int(x) for x in sys.argv[3].split("x")] if len(sys.argv) > 3 else [256, 256]
 mode = sys.argv[4] if len(sys.argv) > 4 else "time"
-name = "pairwise_otf_otf"
+name = os.environ.get("KMOS_B200_PROBE_MODEL", "pairwise_otf_otf")
 ir = tables.load_ir(os.path.join(REPO, "tests", "golden", "models", name + ".json"))
 m = engine.Model(ir=ir)
-rates = workloads.rates_for("pairwise", ir, R)
+rates = workloads.rates_for("pairwise" if name.startswith("pairwise") else "other", ir, R)
 lut = np.tile(otf.build_lut(ir, m.info, rates[0]), (R, 1))
 b = engine.Batch(m, R, size, rates=rates, lut=lut)
 b.do_steps(10)
