@@ -27,7 +27,7 @@ class KmosB200Error(RuntimeError):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_otf.cuh", "kb_otf_fast.cuh", "kb_gen.cuh",
+    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_otf.cuh", "kb_otf_event.cuh", "kb_otf_fast.cuh", "kb_gen.cuh",
                                             "kb_interp.h", "kb_common.h")] + \
         [os.path.join(os.path.dirname(HERE), "include", "kmos_b200.h")]
 
