@@ -700,6 +700,8 @@ def compile_otf_tables(ir, asm):
                     st = stmts[i]
                     writes.append([st[2]] + st[1] + [st[3]] + [0] * 6)
                     i += 1
+                if len(set(tuple(w[1:5]) for w in writes)) != len(writes):
+                    raise Unsupported("%s: two lattice writes on one site" % rname)  # lanes would race
                 while i < len(stmts) and stmts[i][0] == "if_can" and len(stmts[i][3]) == 1 and \
                         stmts[i][3][0][0] == "update_rate":
                     st, u = stmts[i], stmts[i][3][0]

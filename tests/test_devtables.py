@@ -216,7 +216,7 @@ def test_two_replace_species_calls_on_one_site_become_one_write():
 
 
 @pytest.mark.parametrize("name", ["pairwise_otf_otf", "intzgb_otf", "ruo2default_otf", "multidentate_otf", "hop3d_otf",
-                                  "ab_otf", "mini_101_otf"])
+                                  "ab_otf", "mini_101_otf", "zgb_otf", "pt111_otf", "einsd_otf"])
 def test_otf_lane_tables_partition_every_event_routine(name):
     """compile_otf_tables: every statement of run_proc_<proc> ends up in exactly one of the del / write / update
     blocks or in the tail routine, in order, with the operands of the statement."""

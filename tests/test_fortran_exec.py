@@ -110,6 +110,9 @@ FRESH = [
     ("multidentate", "otf", [8, 7], 5000),
     ("pt111", "lat_int", [7, 6], 5000),           # two hollow sites per cell
     ("einsd", "lat_int", [19], 4000),
+    ("zgb", "otf", [8, 7], 5000),
+    ("pt111", "otf", [7, 6], 5000),
+    ("einsd", "otf", [19], 4000),                 # 1-d otf
 ]
 
 EXPORT_DRIVER = r'''

@@ -23,6 +23,8 @@ pytestmark = pytest.mark.gpu
     ("multidentate_otf", [20, 18], [1500, 1500]),        # species spanning two and four sites
     ("hop3d_otf", [8, 7, 6], [1500, 1500]),              # z offsets
     ("ab_otf", [20, 20], [1500, 1500]),
+    ("zgb_otf", [24, 22], [1500, 1500]),
+    ("pt111_otf", [20, 18], [1500, 1500]),               # two hollow sites per cell
 ])
 @pytest.mark.parametrize("lanes", ["lanes", "lanes_routine_tail", "lane0"])
 def test_fast_selection_walks_the_exact_trajectory(name, size, chunks, lanes, monkeypatch):

@@ -175,6 +175,9 @@ OTF_CASES = [
     ("ruo2default_otf", [8, 7], 5, [1500, 1500]),   # the reference's committed otf export: 36 processes, 2 sites/cell
     ("intzgb_otf", [10, 9], 6, [2000, 2000]),        # interacting ZGB: bystander-dependent rates (1150 LUT entries)
     ("multidentate_otf", [8, 7], 5, [2000, 2000]),
+    ("zgb_otf", [12, 10], 5, [2000, 2000]),
+    ("pt111_otf", [8, 7], 5, [2000, 2000]),
+    ("einsd_otf", [23], 5, [2000, 2000]),            # a 1-d otf model
 ]
 
 

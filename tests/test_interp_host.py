@@ -68,6 +68,7 @@ CASES = [
     # multidentate adsorbates (examples/multidentate.py): one species spans two and four sites
     ("multidentate_local_smart", [9, 8], 3000), ("multidentate_lat_int", [8, 7], 3000),
     ("multidentate_otf", [8, 7], 3000),
+    ("zgb_otf", [12, 10], 3000), ("pt111_otf", [8, 7], 3000), ("einsd_otf", [23], 2000),   # 1-d otf
 ]
 
 

@@ -201,7 +201,7 @@ MODELS = [
      ["local_smart", "lat_int", "otf"]),
     ("mini_101", lambda: project_from_ini(MINI_101_INI), ["local_smart", "lat_int", "otf"]),
     ("zgb", lambda: project_from_render_script(os.path.join(REF, "examples/render_ZGB_model.py")),
-     ["local_smart", "lat_int"]),
+     ["local_smart", "lat_int", "otf"]),
     ("ruo2", lambda: project_from_render_script(os.path.join(REF, "examples/render_co_oxidation_ruo2.py")),
      ["local_smart", "lat_int"]),
     ("pairwise", lambda: project_from_render_script(os.path.join(REF, "examples/render_pairwise_interaction.py")),
@@ -228,9 +228,9 @@ MODELS = [
     ("sand", lambda: project_from_render_script(os.path.join(REF, "examples/render_sand_model.py")),
      ["local_smart", "lat_int"]),
     ("pt111", lambda: project_from_render_script(os.path.join(REF, "examples/render_Pt_111.py")),
-     ["local_smart", "lat_int"]),
+     ["local_smart", "lat_int", "otf"]),
     ("einsd", lambda: project_from_render_script(os.path.join(REF, "examples/render_einsD.py")),
-     ["local_smart", "lat_int"]),
+     ["local_smart", "lat_int", "otf"]),
     # multidentate adsorbates: species that occupy two and four sites at once
     ("multidentate", lambda: project_from_render_script(os.path.join(REF, "examples/multidentate.py")),
      ["local_smart", "lat_int", "otf"]),
