@@ -261,11 +261,24 @@ def measure_configs(counters, headline_entry, device, smem_peak, hbm_peak):
                 b.timer_start()
                 b.do_steps(nf)
                 ft.append(b.timer_stop())
+            # what a step has to read: the P row totals, the block sums of the chosen row, one block of 256
+            # entries, and the event's own accesses (taken as config D's figure: the same model's lists)
+            nsf = b.nr_of_sites.astype(np.float64)
+            blocks = np.ceil(nsf / 256.0)
+            live = nsf > 0
+            sel_blocks = float(blocks[live].mean()) if live.any() else 0.0
+            fast_bytes = 8.0 * (len(ir["procs"]) + sel_blocks + 256.0) + 700.0
+            fast_val = R * nf / (float(np.mean(ft)) * 1e-3)
             fast = {"config": "E-fast", "workload": label + ", production selection over block sums (kb_otf_fast.cuh; "
                     "same distribution and prefix order, not bit-exact)", "model": name, "lattice": size,
                     "replicas": R, "kmc_steps_per_launch": nf, "kernel": "otf_fast",
-                    "value": R * nf / (float(np.mean(ft)) * 1e-3), "unit": UNIT, "ms_per_launch": float(np.mean(ft)),
-                    "all_replicas_ok": bool((b.status == 0).all())}
+                    "value": fast_val, "unit": UNIT, "ms_per_launch": float(np.mean(ft)),
+                    "all_replicas_ok": bool((b.status == 0).all()),
+                    "roofline": {"bound": "hbm", "achieved": fast_val * fast_bytes / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": fast_val * fast_bytes / 1e9 / hbm_peak if hbm_peak else None,
+                                 "traffic": None, "algorithmic_bytes_per_kmc_step": fast_bytes,
+                                 "note": "latency-bound: a step is a chain of dependent DRAM round trips over 17 GB "
+                                         "of state (profiles/ncu_otf_fast_kernel_lines_r2b.txt), not a stream"}}
         b.close()
         m.close()
         launch_bytes = b_step * R * n
