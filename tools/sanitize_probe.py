@@ -16,13 +16,17 @@ CASES = [("ruo2_local_smart", [9, 7], capi.KERNEL_GENERATED), ("zgb_local_smart"
          ("mini_101_local_smart", [6, 5], capi.KERNEL_GENERATED), ("pairwise_local_smart", [10, 9], capi.KERNEL_GENERATED),
          ("pairwise_otf_otf", [24, 20], capi.KERNEL_OTF_FAST), ("intzgb_otf", [20, 18], capi.KERNEL_OTF_FAST),
          ("ruo2default_otf", [20, 20], capi.KERNEL_OTF_FAST), ("hop3d_otf", [8, 7, 6], capi.KERNEL_OTF_FAST),
-         ("multidentate_otf", [20, 18], capi.KERNEL_OTF_FAST),
+         ("multidentate_otf", [20, 18], capi.KERNEL_OTF_FAST), ("zgb_otf", [24, 22], capi.KERNEL_OTF_FAST),
+         ("ab_otf", [20, 20], capi.KERNEL_OTF_FAST),
          ("ruo2_local_smart", [9, 7], capi.KERNEL_SMEM), ("zgb_local_smart", [30, 30], capi.KERNEL_SMEM),
          ("ruo2_local_smart", [9, 7], capi.KERNEL_WARP_HBM), ("pairwise_lat_int", [9, 8], capi.KERNEL_WARP_HBM),
          ("pairwise84_lat_int", [9, 8], capi.KERNEL_WARP_HBM), ("pdopd_local_smart", [6, 5], capi.KERNEL_WARP_HBM),
          ("pairwise_otf_otf", [20, 17], capi.KERNEL_WARP_HBM), ("ruo2default_otf", [8, 7], capi.KERNEL_WARP_HBM),
          ("hop3d_local_smart", [5, 6, 5], capi.KERNEL_SMEM), ("ruo2_lat_int", [6, 6], capi.KERNEL_GENERIC)]
+ONLY = sys.argv[1] if len(sys.argv) > 1 else None   # e.g. "otf": cases whose model name contains it
 for name, size, kind in CASES:
+    if ONLY and ONLY not in name:
+        continue
     ir, blob, info = load_model(name)
     R = 11
     rates, lut, seeds = make_inputs(ir, info, R, seed=3)
