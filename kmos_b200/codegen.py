@@ -43,7 +43,7 @@ MAX_COND = 4
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
 # threads per CTA the kernel is compiled for (register budget 65536 / threads): narrow groups run fewer warps
-MAX_THREADS = {32: 768, 16: 640, 8: 512}
+MAX_THREADS = {32: 768, 16: 640, 8: 512, 4: 512}
 
 
 def fnv1a(data):
@@ -138,8 +138,8 @@ def choose_lpr(an):
     step further replicas."""
     env = os.environ.get("KMOS_B200_GEN_LPR")
     if env:
-        if int(env) not in (8, 16, 32):
-            raise ValueError("KMOS_B200_GEN_LPR: 8, 16 or 32")
+        if int(env) not in (4, 8, 16, 32):
+            raise ValueError("KMOS_B200_GEN_LPR: 4, 8, 16 or 32")
         return int(env)
     mean = {}
     for lpr in (32, 16, 8):
@@ -162,6 +162,13 @@ def expected_max_rounds(rounds_per_event, n_groups):
     return float((vals * np.diff(np.concatenate([[0.0], cdf]))).sum())
 
 
+def lane_group_widths(n_proc):
+    """Candidate lanes-per-replica of a model: groups of four lanes (eight replicas per warp) only where a lane
+    then owns at most four processes (registers) -- they pay for models with one or two ops per event
+    (mini_101: +23 % over eight lanes)."""
+    return [4, 8, 16, 32] if n_proc <= 16 else [8, 16, 32]
+
+
 def lane_group_score(n_proc, emax, n_groups, replicas_per_sm):
     """Relative throughput estimate of a lane-group width for one batch geometry (higher is better).
 
@@ -181,6 +188,8 @@ def lane_group_score(n_proc, emax, n_groups, replicas_per_sm):
 def analyse(ir, lpr=None):
     """_flatten + the lane-group width + every event's rounds (ev["rounds"] = [[op, ...], ...])."""
     an = _flatten(ir)
+    if lpr and int(lpr) not in lane_group_widths(an["nproc"]):
+        raise Unsupported("groups of %d lanes per replica with %d processes" % (int(lpr), an["nproc"]))
     an["lpr"] = lpr or choose_lpr(an)
     for ev, rounds in zip(an["events"], _schedule(an, an["lpr"])):
         ev["rounds"] = rounds

@@ -105,13 +105,13 @@ class Batch(object):
             return path
 
         env = os.environ.get("KMOS_B200_GEN_LPR")
-        widths = [int(lpr)] if lpr else ([int(env)] if env else [8, 16, 32])
         try:
             an = codegen._flatten(self.model.ir)
         except devtables.Unsupported:
             if proclist == "build":
                 raise
             return None
+        widths = [int(lpr)] if lpr else ([int(env)] if env else codegen.lane_group_widths(an["nproc"]))
         # How many replicas a lane-group width keeps resident depends on the lattice: attach every candidate
         # width once, score it (codegen.lane_group_score), keep the best.
         best = None

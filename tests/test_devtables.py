@@ -181,14 +181,22 @@ def test_lane_group_width_model():
     assert codegen.expected_max_rounds([3, 3, 3], 4) == 3.0
     assert abs(codegen.expected_max_rounds([1, 3], 2) - 2.5) < 1e-12        # P(max = 1) = 1/4
     assert codegen.expected_max_rounds([], 2) == 0.0
-    measured_best = {"ruo2": ((32, 32, 24), (8,)), "zgb": ((24, 26, 24), (16,)), "pairwise": ((24, 24, 24), (16,)),
-                     "ab": ((64, 40, 24), (8,)), "mini_101": ((128, 40, 24), (8,)),
-                     "ruo2 ": ((14, 14, 14), (16,))}      # a 2048-replica shard: 14 replicas per SM at any width
+    # resident replicas per SM at 4 / 8 / 16 / 32 lanes per replica (None: width not offered), measured best
+    measured_best = {"ruo2": ((None, 32, 32, 24), (8,)), "zgb": ((None, 24, 26, 24), (16,)),
+                     "pairwise": ((None, 24, 24, 24), (16,)),
+                     "ab": ((72, 64, 40, 24), (4, 8)),          # 5.99e9 and 5.97e9: a tie
+                     "mini_101": ((80, 64, 40, 24), (4,)),      # 8.9e9 against 7.2e9 at 8 lanes
+                     "ruo2 ": ((None, 14, 14, 14), (16,))}      # a 2048-replica shard: 14 replicas per SM at any width
+    assert codegen.lane_group_widths(2) == [4, 8, 16, 32] and codegen.lane_group_widths(36) == [8, 16, 32]
+    with pytest.raises(dt.Unsupported):
+        codegen.analyse(load_model("ruo2_local_smart")[0], 4)
     for name, (resident, best) in measured_best.items():
         ir, _blob, _info = load_model(name.strip() + "_local_smart")
         an = codegen._flatten(ir)
         scores = {}
-        for w, reps in zip((8, 16, 32), resident):
+        for w, reps in zip((4, 8, 16, 32), resident):
+            if reps is None:
+                continue
             rounds = [len(r) for r in codegen._schedule(an, w)]
             assert max(len(x) for r in codegen._schedule(an, w) for x in r) <= w
             scores[w] = codegen.lane_group_score(an["nproc"], codegen.expected_max_rounds(rounds, 32 // w), 32 // w, reps)

@@ -62,7 +62,7 @@ def test_local_smart_parity(name, size, R, chunks, kernel):
     batch.close()
 
 
-@pytest.mark.parametrize("lpr", [8, 16, 32])
+@pytest.mark.parametrize("lpr", [4, 8, 16, 32])
 @pytest.mark.parametrize("name,size,R,chunks", [
     ("ruo2_local_smart", [20, 20], 7, [3000, 3000]),   # 7 replicas: the last team of 2 / 4 is incomplete
     ("ruo2_local_smart", [5, 7], 9, [3000, 3000]),
@@ -70,12 +70,17 @@ def test_local_smart_parity(name, size, R, chunks, kernel):
     ("pairwise_local_smart", [10, 9], 5, [2000, 2000]),
     ("ab_local_smart", [20, 20], 33, [500, 2500]),
     ("hop3d_local_smart", [5, 6, 5], 6, [2000]),
+    ("mini_101_local_smart", [6, 5], 19, [1000, 1000]),  # 19 replicas: three teams of eight at 4 lanes, the last incomplete
+    ("multidentate_local_smart", [9, 8], 9, [2000]),
 ])
 def test_generated_kernel_lane_group_widths(name, size, R, chunks, lpr):
     """The generated kernel steps 32/lpr replicas per warp in lock step; every width must walk the oracle's
     trajectory, with replica counts that leave the last team incomplete."""
     engine = _engine()
+    from kmos_b200 import codegen
     ir, blob, info = load_model(name)
+    if lpr not in codegen.lane_group_widths(len(ir["procs"])):
+        pytest.skip("groups of %d lanes are for models with at most 16 processes" % lpr)
     rates, lut, seeds = make_inputs(ir, info, R, seed=len(name) + lpr)
     model = engine.Model(ir=ir, blob=blob, info=info)
     batch = engine.Batch(model, R, size, seeds=seeds, rates=rates, kernel=capi.KERNEL_GENERATED, lpr=lpr)

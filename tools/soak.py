@@ -18,10 +18,11 @@ from conftest import load_model  # noqa: E402
 from util import make_inputs, oracle_checkpoints  # noqa: E402
 from kmos_b200 import capi, devtables, engine  # noqa: E402
 
-KERNELS = {"local_smart": ["gen8", "gen16", "gen32", "smem", "warp_hbm", "generic"], "lat_int": ["warp_hbm", "generic"],
+KERNELS = {"local_smart": ["gen4", "gen8", "gen16", "gen32", "smem", "warp_hbm", "generic"], "lat_int": ["warp_hbm", "generic"],
            "otf": ["warp_hbm", "generic"]}
 KIND = {"smem": capi.KERNEL_SMEM, "warp_hbm": capi.KERNEL_WARP_HBM, "generic": capi.KERNEL_GENERIC,
-        "gen8": capi.KERNEL_GENERATED, "gen16": capi.KERNEL_GENERATED, "gen32": capi.KERNEL_GENERATED}
+        "gen4": capi.KERNEL_GENERATED, "gen8": capi.KERNEL_GENERATED, "gen16": capi.KERNEL_GENERATED,
+        "gen32": capi.KERNEL_GENERATED}
 
 
 def main():
