@@ -77,6 +77,34 @@ def test_config4_pairwise_otf_256x256():
     _check_sample(b, blob, [256, 256], seeds, rates, lut, n, [0, 7], avail=True)
 
 
+@pytest.mark.parametrize("lanes", ["lanes", "lane0"])
+def test_config4_on_the_production_kernel_256x256(lanes, monkeypatch):
+    """Config E's lattice on kb_otf_fast.cuh: 65 536 cells, i.e. the 32-bit list instantiation the bench runs and
+    256 blocks per row -- the small lattices of tests/test_gpu_otf_fast.py use 16-bit lists.  Over 400 steps from
+    the empty lattice the selection coincides with the exact one: lattice, counts and lists bit for bit."""
+    from kmos_b200 import capi, engine
+    from oracle import oracle
+    monkeypatch.setenv("KMOS_B200_OTF_LANES", "1" if lanes == "lanes" else "0")
+    ir, blob, info = load_model("pairwise_otf_otf")
+    R, n = 6, 400
+    rates = workloads.rates_for("pairwise_otf", ir, R)
+    lut = np.stack([otf_mod.build_lut(ir, info, rates[r]) for r in range(R)])
+    seeds = np.arange(R, dtype=np.uint64) + np.uint64(17)
+    b = engine.Batch(engine.Model(ir=ir, blob=blob, info=info), R, [256, 256], seeds=seeds, rates=rates, lut=lut,
+                     kernel=capi.KERNEL_OTF_FAST)
+    assert b.kernel_info()["kernel_name"] == "otf_fast"
+    b.do_steps(n)
+    assert np.all(b.status == 0) and np.all(b.kmc_step == n) and np.all(b.procstat.sum(axis=1) == n)
+    for r in (0, R - 1):
+        o = oracle.Oracle(blob, [256, 256], seed=int(seeds[r]), replica=r, rates=rates[r], lut=lut[r])
+        assert o.do_steps(n) == 0
+        assert np.array_equal(b.lattice[r], o.lattice) and np.array_equal(b.procstat[r], o.procstat)
+        assert np.array_equal(b.nr_of_sites[r], o.nr_of_sites)
+        assert np.array_equal(b.avail_sites(r), o.avail_sites)
+        assert abs(b.kmc_time[r] - o.kmc_time) <= 1e-9 * o.kmc_time
+    b.close()
+
+
 def test_production_stream_statistics_within_3_sigma():
     """north_star: production-stream runs must agree statistically with the reference.  GPU ensemble (one set
     of Philox keys) vs CPU-oracle ensemble (a disjoint set of keys) of the ZGB model at y_CO = 0.45: the mean
