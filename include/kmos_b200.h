@@ -180,6 +180,40 @@ int kmos_b200_tally_words(const kmos_b200_batch *b);
 int kmos_b200_reduce_tallies(kmos_b200_batch *b, const int32_t *group_of, int32_t n_groups, void *dev_out,
                              double *host_out);
 
+/* ---- fleet: R replicas of one model sharded over several GPUs of ONE process -----------------------------
+ * replaces: nothing in the reference (its one trajectory per process is spread by ModelRunner.run(cores=N),
+ * kmos/run/__init__.py:2330-2366, a multiprocessing pool); SURVEY 8b's `gpu_ids[], n_gpus` arguments.  For callers
+ * that are not launched one process per GPU -- the Fortran templates over ISO_C_BINDING, a plain Python session.
+ * Shard k of n_gpus holds replicas [R*k/n_gpus, R*(k+1)/n_gpus) as an ordinary batch on gpu_ids[k]; a device may
+ * be named more than once.  seeds[R] (NULL: 0..R-1) are Philox keys, the counter carries the global replica
+ * number, so trajectories do not depend on n_gpus.  do_kmc_steps enqueues on every GPU and returns; getters take
+ * [R]-leading host buffers exactly like the batch getters and synchronise.  Everything else (set_configuration,
+ * avail_sites, restart, ...) goes through kmos_b200_fleet_shard(k) and the batch API. */
+typedef struct kmos_b200_fleet kmos_b200_fleet;
+int kmos_b200_fleet_create(kmos_b200_model *m, int32_t n_replicas, const int32_t size[3], const uint64_t *seeds,
+                           const int32_t *gpu_ids, int32_t n_gpus, kmos_b200_fleet **out);
+void kmos_b200_fleet_destroy(kmos_b200_fleet *f);
+int kmos_b200_fleet_n_shards(const kmos_b200_fleet *f); /* <= n_gpus: GPUs without a replica hold no shard */
+kmos_b200_batch *kmos_b200_fleet_shard(kmos_b200_fleet *f, int32_t k, int32_t *first_replica, int32_t *n_replicas);
+int kmos_b200_fleet_attach_proclist(kmos_b200_fleet *f, const char *so_path);
+int kmos_b200_fleet_select_kernel(kmos_b200_fleet *f, int32_t kind);
+int kmos_b200_fleet_set_rates(kmos_b200_fleet *f, const double *rates /*[R][P]*/);
+int kmos_b200_fleet_set_otf_lut(kmos_b200_fleet *f, const double *lut /*[R][lut_size]*/);
+int kmos_b200_fleet_init_state(kmos_b200_fleet *f, int32_t layer);
+int kmos_b200_fleet_do_kmc_steps(kmos_b200_fleet *f, int64_t n);
+int kmos_b200_fleet_synchronize(kmos_b200_fleet *f);
+int kmos_b200_fleet_get_kmc_time(kmos_b200_fleet *f, double *out /*[R]*/);
+int kmos_b200_fleet_get_kmc_step(kmos_b200_fleet *f, int64_t *out /*[R]*/);
+int kmos_b200_fleet_get_status(kmos_b200_fleet *f, int32_t *out /*[R]*/);
+int kmos_b200_fleet_get_procstat(kmos_b200_fleet *f, int64_t *out /*[R][P]*/);
+int kmos_b200_fleet_get_integ_rates(kmos_b200_fleet *f, double *out /*[R][P]*/);
+int kmos_b200_fleet_get_nr_of_sites(kmos_b200_fleet *f, int32_t *out /*[R][P]*/);
+int kmos_b200_fleet_get_lattice(kmos_b200_fleet *f, int32_t *out /*[R][V]*/);
+int kmos_b200_fleet_get_occupation(kmos_b200_fleet *f, double *out /*[R][n_species][spuck]*/);
+/* kmos_b200_reduce_tallies over all shards: group_of[R] (NULL: one group), host_out[n_groups][tally_words];
+ * per-GPU device reductions, partial sums added on the host in shard order. */
+int kmos_b200_fleet_reduce_tallies(kmos_b200_fleet *f, const int32_t *group_of, int32_t n_groups, double *host_out);
+
 /* Validation hook shared with a Fortran validation build: the uniform number `slot` (0 ran_time,
  * 1 ran_proc, 2 ran_site) of kMC step `step` -- what `call random_number(x)` is rewritten to
  * (pattern: kmos/utils/__init__.py:818-829). */

@@ -27,7 +27,7 @@ class KmosB200Error(RuntimeError):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_otf.cuh", "kb_otf_event.cuh", "kb_otf_fast.cuh", "kb_gen.cuh",
+    return [os.path.join(CSRC, f) for f in ("kmos_b200.cu", "kb_smem.cuh", "kb_latint.cuh", "kb_otf.cuh", "kb_otf_event.cuh", "kb_otf_fast.cuh", "kb_gen.cuh", "kb_fleet.h",
                                             "kb_interp.h", "kb_common.h")] + \
         [os.path.join(os.path.dirname(HERE), "include", "kmos_b200.h")]
 
@@ -138,6 +138,27 @@ def lib():
         "kmos_b200_philox_next": (f64, [u64, u32, u64, i32]),
         "kmos_b200_batch_set_stream": (C.c_int, [vp, vp]),
         "kmos_b200_measure_smem_bandwidth": (C.c_int, [i32, C.POINTER(f64), C.POINTER(f64)]),
+        # fleet: the same replicas on several GPUs of this process (csrc/kb_fleet.h)
+        "kmos_b200_fleet_create": (C.c_int, [vp, i32, arr(np.int32), vp, arr(np.int32), i32, C.POINTER(vp)]),
+        "kmos_b200_fleet_destroy": (None, [vp]),
+        "kmos_b200_fleet_n_shards": (C.c_int, [vp]),
+        "kmos_b200_fleet_shard": (vp, [vp, i32, C.POINTER(i32), C.POINTER(i32)]),
+        "kmos_b200_fleet_attach_proclist": (C.c_int, [vp, C.c_char_p]),
+        "kmos_b200_fleet_select_kernel": (C.c_int, [vp, i32]),
+        "kmos_b200_fleet_set_rates": (C.c_int, [vp, arr(np.float64)]),
+        "kmos_b200_fleet_set_otf_lut": (C.c_int, [vp, arr(np.float64)]),
+        "kmos_b200_fleet_init_state": (C.c_int, [vp, i32]),
+        "kmos_b200_fleet_do_kmc_steps": (C.c_int, [vp, i64]),
+        "kmos_b200_fleet_synchronize": (C.c_int, [vp]),
+        "kmos_b200_fleet_get_kmc_time": (C.c_int, [vp, arr(np.float64)]),
+        "kmos_b200_fleet_get_kmc_step": (C.c_int, [vp, arr(np.int64)]),
+        "kmos_b200_fleet_get_status": (C.c_int, [vp, arr(np.int32)]),
+        "kmos_b200_fleet_get_procstat": (C.c_int, [vp, arr(np.int64)]),
+        "kmos_b200_fleet_get_integ_rates": (C.c_int, [vp, arr(np.float64)]),
+        "kmos_b200_fleet_get_nr_of_sites": (C.c_int, [vp, arr(np.int32)]),
+        "kmos_b200_fleet_get_lattice": (C.c_int, [vp, arr(np.int32)]),
+        "kmos_b200_fleet_get_occupation": (C.c_int, [vp, arr(np.float64)]),
+        "kmos_b200_fleet_reduce_tallies": (C.c_int, [vp, vp, i32, arr(np.float64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -161,6 +182,13 @@ EXPORTED = [
     "kmos_b200_reduce_tallies", "kmos_b200_philox_next", "kmos_b200_batch_set_stream",
     "kmos_b200_measure_smem_bandwidth", "kmos_b200_get_next_kmc_step", "kmos_b200_run_proc_nr",
     "kmos_b200_reload_replica", "kmos_b200_batch_attach_proclist", "kmos_b200_batch_detach_proclist",
+    "kmos_b200_fleet_create", "kmos_b200_fleet_destroy", "kmos_b200_fleet_n_shards", "kmos_b200_fleet_shard",
+    "kmos_b200_fleet_attach_proclist", "kmos_b200_fleet_select_kernel", "kmos_b200_fleet_set_rates",
+    "kmos_b200_fleet_set_otf_lut", "kmos_b200_fleet_init_state", "kmos_b200_fleet_do_kmc_steps",
+    "kmos_b200_fleet_synchronize", "kmos_b200_fleet_get_kmc_time", "kmos_b200_fleet_get_kmc_step",
+    "kmos_b200_fleet_get_status", "kmos_b200_fleet_get_procstat", "kmos_b200_fleet_get_integ_rates",
+    "kmos_b200_fleet_get_nr_of_sites", "kmos_b200_fleet_get_lattice", "kmos_b200_fleet_get_occupation",
+    "kmos_b200_fleet_reduce_tallies",
 ]
 
 

@@ -1450,3 +1450,5 @@ extern "C" int kmos_b200_measure_smem_bandwidth(int32_t device, double* gbps, do
     if (sm_mhz) *sm_mhz = prop.clockRate / 1000.0;
     return KMOS_B200_OK;
 }
+
+#include "kb_fleet.h"  // kmos_b200_fleet_*: the same replicas dealt to several GPUs of this process

@@ -316,6 +316,162 @@ class Batch(object):
             pass
 
 
+class _ShardView(Batch):
+    """A fleet's shard seen through the Batch interface (borrowed handle: the fleet destroys it)."""
+
+    def __init__(self, model, handle, n_replicas, size3, layer):
+        self.L = capi.lib()
+        self.model = model
+        self.R = int(n_replicas)
+        self.size = size3
+        self.h = handle
+        self.P = model.n_proc
+        self.volume = self.L.kmos_b200_batch_volume(handle)
+        self.ncells = self.volume // model.spuck
+        self.layer = layer
+        self.proclist = None
+
+    def close(self):
+        self.h = None
+
+
+class Fleet(object):
+    """R replicas of one model dealt to several GPUs of THIS process (kmos_b200_fleet_*, csrc/kb_fleet.h): the
+    single-process counterpart of one Batch per torchrun rank.  gpu_ids: one entry per shard (default: every
+    visible GPU); shard k holds replicas parallel.shard_bounds(R, k, len(gpu_ids)).  Same observables as Batch, in
+    global replica order; trajectories do not depend on the number of shards (Philox counters carry the global
+    replica number).  ``shards[k]`` is a Batch view for everything the fleet API does not forward."""
+
+    def __init__(self, model, n_replicas, size, gpu_ids=None, seeds=None, rates=None, lut=None,
+                 kernel=capi.KERNEL_AUTO, init=True, layer=None, proclist="auto", lpr=None):
+        self.L = capi.lib()
+        self.model = model
+        self.R = int(n_replicas)
+        size3 = np.ones(3, dtype=np.int32)
+        size = np.atleast_1d(np.asarray(size, dtype=np.int32))
+        size3[:len(size)] = size
+        self.size = size3
+        if gpu_ids is None:
+            gpu_ids = list(range(max(self.L.kmos_b200_device_count(), 1)))
+        self.gpu_ids = np.ascontiguousarray(gpu_ids, dtype=np.int32)
+        s = None
+        if seeds is not None:
+            s = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (self.R,)))
+        h = C.c_void_p()
+        capi.check(self.L.kmos_b200_fleet_create(model.h, self.R, size3, s.ctypes.data_as(C.c_void_p) if s is not None
+                                                 else None, self.gpu_ids, int(self.gpu_ids.size), C.byref(h)))
+        self.h = h
+        self.P = model.n_proc
+        self.layer = model.default_layer if layer is None else int(layer)
+        self.shards, self.bounds = [], []
+        for k in range(self.L.kmos_b200_fleet_n_shards(h)):
+            lo, n = C.c_int32(0), C.c_int32(0)
+            bh = self.L.kmos_b200_fleet_shard(h, k, C.byref(lo), C.byref(n))
+            self.shards.append(_ShardView(model, C.c_void_p(bh), n.value, size3, self.layer))
+            self.bounds.append((lo.value, lo.value + n.value))
+        self.volume = self.shards[0].volume
+        self.ncells = self.shards[0].ncells
+        if kernel == capi.KERNEL_GENERATED and proclist in (None, "auto"):
+            proclist = "build"
+        if proclist and (proclist not in ("auto", "build") or
+                         (model.backend == capi.BACKEND_LOCAL_SMART and model.ir is not None)):
+            for sh in self.shards:  # per shard: the best lane-group width depends on the shard's replica count
+                sh.attach_proclist(proclist, lpr)
+        if kernel != capi.KERNEL_AUTO:
+            self.select_kernel(kernel)
+        if rates is not None:
+            self.set_rates(rates)
+        if lut is not None:
+            self.set_otf_lut(lut)
+        if init:
+            self.init_state()
+
+    def select_kernel(self, kind):
+        capi.check(self.L.kmos_b200_fleet_select_kernel(self.h, int(kind)))
+
+    def kernel_info(self):
+        return [sh.kernel_info() for sh in self.shards]
+
+    def set_rates(self, rates):
+        r = np.asarray(rates, dtype=np.float64)
+        if r.ndim == 1:
+            r = np.broadcast_to(r, (self.R, self.P))
+        r = np.ascontiguousarray(r)
+        assert r.shape == (self.R, self.P)
+        capi.check(self.L.kmos_b200_fleet_set_rates(self.h, r))
+        self._rates_host = r
+
+    def set_otf_lut(self, lut):
+        t = np.asarray(lut, dtype=np.float64)
+        if t.ndim == 1:
+            t = np.broadcast_to(t, (self.R, t.size))
+        t = np.ascontiguousarray(t)
+        assert t.shape == (self.R, self.model.lut_size)
+        capi.check(self.L.kmos_b200_fleet_set_otf_lut(self.h, t))
+        self._lut_host = t
+
+    def init_state(self, layer=None):
+        capi.check(self.L.kmos_b200_fleet_init_state(self.h, self.layer if layer is None else int(layer)))
+
+    def do_steps(self, n):
+        """Enqueue n kMC steps on every GPU; returns at once, the getters synchronise."""
+        capi.check(self.L.kmos_b200_fleet_do_kmc_steps(self.h, int(n)))
+
+    def synchronize(self):
+        capi.check(self.L.kmos_b200_fleet_synchronize(self.h))
+
+    def _get(self, name, shape, dtype):
+        out = np.zeros(shape, dtype=dtype)
+        capi.check(getattr(self.L, "kmos_b200_fleet_get_" + name)(self.h, out))
+        return out
+
+    kmc_time = property(lambda self: self._get("kmc_time", self.R, np.float64))
+    kmc_step = property(lambda self: self._get("kmc_step", self.R, np.int64))
+    status = property(lambda self: self._get("status", self.R, np.int32))
+    procstat = property(lambda self: self._get("procstat", (self.R, self.P), np.int64))
+    integ_rates = property(lambda self: self._get("integ_rates", (self.R, self.P), np.float64))
+    nr_of_sites = property(lambda self: self._get("nr_of_sites", (self.R, self.P), np.int32))
+    lattice = property(lambda self: self._get("lattice", (self.R, self.volume), np.int32))
+    occupation = property(lambda self: self._get("occupation", (self.R, self.model.n_species, self.model.spuck),
+                                                 np.float64))
+
+    def avail_sites(self, replica):
+        for sh, (lo, hi) in zip(self.shards, self.bounds):
+            if lo <= replica < hi:
+                return sh.avail_sites(replica - lo)
+        raise IndexError(replica)
+
+    def tally_words(self):
+        return self.shards[0].tally_words()
+
+    def reduce_tallies(self, group_of=None, n_groups=1):
+        """Per-group sums over all shards (layout: include/kmos_b200.h, split_tally)."""
+        g = None
+        if group_of is not None:
+            g = np.ascontiguousarray(group_of, dtype=np.int32)
+            assert g.size == self.R
+        host = np.zeros((n_groups, self.tally_words()))
+        capi.check(self.L.kmos_b200_fleet_reduce_tallies(
+            self.h, g.ctypes.data_as(C.c_void_p) if g is not None else None, int(n_groups), host))
+        return host
+
+    def split_tally(self, t):
+        return self.shards[0].split_tally(t)
+
+    def close(self):
+        if getattr(self, "h", None):
+            for sh in self.shards:
+                sh.close()
+            self.L.kmos_b200_fleet_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def measure_smem_bandwidth(device=0):
     """(GB/s, SM clock MHz) of the shared-memory streaming microbenchmark."""
     gb, mhz = C.c_double(0), C.c_double(0)
