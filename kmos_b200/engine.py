@@ -435,11 +435,69 @@ class Fleet(object):
     occupation = property(lambda self: self._get("occupation", (self.R, self.model.n_species, self.model.spuck),
                                                  np.float64))
 
-    def avail_sites(self, replica):
+    # ---- the rest of the Batch interface, forwarded shard by shard (kmos_b200_fleet_shard + the batch API) ----
+    def _cat(self, name):
+        return np.concatenate([getattr(sh, name) for sh in self.shards], axis=0)
+
+    kmc_time_step = property(lambda self: self._cat("kmc_time_step"))
+    accum_rates = property(lambda self: self._cat("accum_rates"))
+    rates = property(lambda self: self._cat("rates"))
+    error_info = property(lambda self: self._cat("error_info"))
+
+    def _owner(self, replica):
+        """(shard, local index) of global replica `replica`."""
+        replica = int(replica)
         for sh, (lo, hi) in zip(self.shards, self.bounds):
             if lo <= replica < hi:
-                return sh.avail_sites(replica - lo)
+                return sh, replica - lo
         raise IndexError(replica)
+
+    def _rows(self, a, dtype):
+        """A per-replica argument (scalars are broadcast) cut into the shards' blocks."""
+        a = np.asarray(a, dtype)
+        a = np.broadcast_to(a, (self.R,) + a.shape[1:]) if a.ndim <= 1 else a
+        assert a.shape[0] == self.R
+        return [np.ascontiguousarray(a[lo:hi]) for lo, hi in self.bounds]
+
+    def set_rate_const(self, proc, rate, replica=-1):
+        if replica < 0:
+            for sh in self.shards:
+                sh.set_rate_const(proc, rate)
+        else:
+            sh, r = self._owner(replica)
+            sh.set_rate_const(proc, rate, replica=r)
+
+    def set_configuration(self, species, replica=-1, layer=None):
+        if replica >= 0:
+            sh, r = self._owner(replica)
+            return sh.set_configuration(species, replica=r, layer=layer)
+        s = np.asarray(species, dtype=np.int32).reshape(self.R, self.volume)
+        for sh, (lo, hi) in zip(self.shards, self.bounds):
+            sh.set_configuration(s[lo:hi], layer=layer)
+
+    def get_next_kmc_step(self):
+        got = [sh.get_next_kmc_step() for sh in self.shards]
+        return np.concatenate([g[0] for g in got]), np.concatenate([g[1] for g in got])
+
+    def run_proc_nr(self, proc, site):
+        for sh, p, q in zip(self.shards, self._rows(proc, np.int32), self._rows(site, np.int32)):
+            sh.run_proc_nr(p, q)
+
+    def set_kmc_time(self, t):
+        for sh, x in zip(self.shards, self._rows(t, np.float64)):
+            sh.set_kmc_time(x)
+
+    def save_system(self, path, replica=0):
+        sh, r = self._owner(replica)
+        sh.save_system(path, r)
+
+    def reload_system(self, path, replica=0):
+        sh, r = self._owner(replica)
+        sh.reload_system(path, r)
+
+    def avail_sites(self, replica):
+        sh, r = self._owner(replica)
+        return sh.avail_sites(r)
 
     def tally_words(self):
         return self.shards[0].tally_words()

@@ -29,14 +29,16 @@ class _Namespace(object):
 
 class KMC_Model(object):
     def __init__(self, model, size=20, n_replicas=1, seeds=None, parameters=None, device=0, kernel=capi.KERNEL_AUTO,
-                 random_seed=1, mu=None, cache_file=None, replica_ids=None):
+                 random_seed=1, mu=None, cache_file=None, replica_ids=None, gpu_ids=None):
         """model: path of a rule-table JSON (what the exporter hook writes) or a parsed IR dict.
         parameters: dict of overrides, or a list of R dicts (one parameter point per replica).
         mu: chemical potentials for ``mu_<gas>`` tokens: a ``kmos.species``-compatible provider or a callable
         (gas, T, p) -> eV.  Default: the reference's kmos.species if importable, else the closed-form stand-in
         of kmos_b200.rates with a MuStandinWarning (rate constants then differ from the reference's).
         replica_ids: the replicas' indices in the Philox counter (default 0..R-1); a sweep sharded over several
-        batches passes its global indices so that the shards reproduce the unsharded run."""
+        batches passes its global indices so that the shards reproduce the unsharded run.
+        gpu_ids: deal the replicas to these GPUs from this one process (engine.Fleet, kmos_b200_fleet_*) instead
+        of running them on `device`; every replica steps exactly as it does on a single GPU."""
         self.ir = tables.load_ir(model) if isinstance(model, str) else model
         self.model = engine.Model(ir=self.ir)
         dim = self.ir["model_dimension"]
@@ -51,9 +53,16 @@ class KMC_Model(object):
             self._overrides = [dict(parameters or {}) for _ in range(self.R)]
         if seeds is None:
             seeds = np.uint64(random_seed) + np.arange(self.R, dtype=np.uint64)
-        self.batch = engine.Batch(self.model, self.R, self.size[:dim].astype(np.int32), device=device, seeds=seeds,
-                                  replica_ids=replica_ids,
-                                  rates=self._evaluate_rates(), lut=self._evaluate_lut(), kernel=kernel)
+        if gpu_ids is not None:
+            if replica_ids is not None:
+                raise ValueError("gpu_ids and replica_ids are exclusive: a fleet numbers its replicas 0..R-1")
+            self.batch = engine.Fleet(self.model, self.R, self.size[:dim].astype(np.int32), gpu_ids=gpu_ids,
+                                      seeds=seeds, rates=self._evaluate_rates(), lut=self._evaluate_lut(),
+                                      kernel=kernel)
+        else:
+            self.batch = engine.Batch(self.model, self.R, self.size[:dim].astype(np.int32), device=device,
+                                      seeds=seeds, replica_ids=replica_ids,
+                                      rates=self._evaluate_rates(), lut=self._evaluate_lut(), kernel=kernel)
         self.species_names = list(self.ir["species"])
         self.site_names = list(self.ir["sites"])
         self.process_names = list(self.ir["procs"])
@@ -188,7 +197,7 @@ class KMC_Model(object):
         if overrun.any() and reset_time_overrun:
             t = a.kmc_time.copy()
             t[overrun] = 0.0
-            capi.check(b.L.kmos_b200_set_kmc_time(b.h, np.ascontiguousarray(t)))
+            b.set_kmc_time(t)
             a.tof_data[overrun] = 0.0
             a.tof_integ[overrun] = 0.0
         a.delta_t = delta_t

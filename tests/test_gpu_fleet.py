@@ -78,3 +78,52 @@ def test_fleet_fewer_replicas_than_gpus_and_errors():
         engine.Fleet(model, 4, [6, 6], gpu_ids=[0, 99])
     with pytest.raises(capi.KmosB200Error):
         engine.Fleet(model, 4, [6, 6], gpu_ids=[])
+
+
+def test_kmc_model_on_a_fleet_gives_the_single_gpu_rows(tmp_path):
+    """KMC_Model(gpu_ids=...) -- the front-end of one process on several GPUs: the reference-shaped outputs, the
+    replay entry points and the configuration round trip are those of the same replicas on one batch (which
+    tests/test_gpu_model.py holds against the oracle)."""
+    import os
+    from conftest import GOLDEN
+    from kmos_b200.model import KMC_Model
+    path = os.path.join(GOLDEN, "models", "ab_local_smart.json")
+    points = [{"p_COgas": 1.0, "p_O2gas": 1.0}, {"p_COgas": 0.3, "p_O2gas": 2.0}, {"p_COgas": 3.0, "p_O2gas": 0.5},
+              {"p_COgas": 2.0, "p_O2gas": 0.7}, {"p_COgas": 0.5, "p_O2gas": 0.5}]
+    n_dev = capi.lib().kmos_b200_device_count()
+    kw = dict(size=[12, 10], n_replicas=5, parameters=points, random_seed=5)
+    with KMC_Model(path, **kw) as one, KMC_Model(path, gpu_ids=[0, 1 % n_dev, 0], **kw) as many:
+        assert [hi - lo for lo, hi in many.batch.bounds] == [1, 2, 2]
+        for m in (one, many):
+            m.do_steps(2000)
+        a = one.get_std_sampled_data_all(samples=3, sample_size=3000, tof_method="integ")
+        b = many.get_std_sampled_data_all(samples=3, sample_size=3000, tof_method="integ")
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+        # get_next_kmc_step / run_proc_nr (the replay loop of tests/test_run/test_run.py) across shards
+        for _ in range(20):
+            pa, sa = one.batch.get_next_kmc_step()
+            pb, sb = many.batch.get_next_kmc_step()
+            assert np.array_equal(pa, pb) and np.array_equal(sa, sb)
+            one.batch.run_proc_nr(pa, sa)
+            many.batch.run_proc_nr(pb, sb)
+        assert np.array_equal(one.batch.lattice, many.batch.lattice)
+        # configuration of a replica in the last shard into one of the first; set_rate_const on one replica
+        many.dump_config(str(tmp_path / "cfg"), replica=4)
+        many.load_config(str(tmp_path / "cfg"), replica=0)
+        one.dump_config(str(tmp_path / "cfg1"), replica=4)
+        one.load_config(str(tmp_path / "cfg1"), replica=0)
+        for m in (one, many):
+            m.batch.set_rate_const(1, 0.125, replica=3)
+            m.batch.set_kmc_time(np.arange(5.0))
+            m.do_steps(1500)
+        assert many.batch.rates[3, 0] == 0.125 and many.batch.rates[2, 0] != 0.125
+        for name in ("lattice", "procstat", "kmc_time", "kmc_step", "nr_of_sites", "accum_rates", "kmc_time_step"):
+            assert np.array_equal(getattr(one.batch, name), getattr(many.batch, name)), name
+        assert np.array_equal(one.batch.avail_sites(4), many.batch.avail_sites(4))
+        # restart file of a replica that lives on the second shard
+        many.batch.save_system(str(tmp_path / "r.reload"), replica=2)
+        many.do_steps(700)
+        ref = many.batch.lattice[2].copy()
+        many.batch.reload_system(str(tmp_path / "r.reload"), replica=2)
+        many.do_steps(700)
+        assert np.array_equal(many.batch.lattice[2], ref)
