@@ -51,6 +51,8 @@ def test_no_cpu_fallback(built):
     model = engine.Model(ir=ir, blob=blob, info=info)
     with pytest.raises(capi.KmosB200Error, match="no CUDA device"):
         engine.Batch(model, 4, [4, 4])
+    with pytest.raises(capi.KmosB200Error, match="no CUDA device"):
+        engine.Fleet(model, 4, [4, 4], gpu_ids=[0, 1])
 
 
 def test_product_package_never_imports_the_oracle():
