@@ -76,16 +76,21 @@ class LinearParameter(ModelParameter):
 
 
 def _run_points(model_path, size, seeds, points, first_point, device, init_steps, sample_steps, samples,
-                random_seed, model_factory=None):
+                random_seed, model_factory=None, gpu_ids=None):
     """The rows of `points` (grid points first_point, first_point+1, ... of the whole scan), `seeds` replicas
     each, as one batch on one GPU.  Philox keys follow the *global* replica index, so a scan gives the same
-    rows however its points are dealt to GPUs.  -> (header, rows[len(points)*seeds][fields], parameter dump)"""
+    rows however its points are dealt to GPUs.  gpu_ids: the whole scan (first_point 0) as one fleet of this
+    process (engine.Fleet) instead.  -> (header, rows[len(points)*seeds][fields], parameter dump)"""
     per_rep = [pt for pt in points for _ in range(seeds)]
     gid = first_point * seeds + np.arange(len(per_rep))
     keys = (np.uint64(random_seed) + gid.astype(np.uint64))
     factory = model_factory or KMC_Model
-    with factory(model_path, size=size, n_replicas=len(per_rep), parameters=per_rep, device=device,
-                 seeds=keys, replica_ids=gid.astype(np.uint32)) as model:
+    if gpu_ids is not None:
+        assert first_point == 0
+        where = dict(gpu_ids=list(gpu_ids))
+    else:
+        where = dict(device=device, replica_ids=gid.astype(np.uint32))
+    with factory(model_path, size=size, n_replicas=len(per_rep), parameters=per_rep, seeds=keys, **where) as model:
         model.do_steps(int(init_steps))
         model.get_atoms_all()
         rows = model.get_std_sampled_data_all(samples, int(sample_steps), tof_method="integ")
@@ -110,7 +115,8 @@ class ModelRunner(object):
     API mirror of kmos.run.ModelRunner (kmos/run/__init__.py:2005-2366): the reference's ``run(cores=N)`` deals
     grid points to a pool of N processes that append to one ``.dat`` file under a lock file; ``run(gpus=N)``
     deals contiguous blocks of grid points (kmos_b200.parallel.shard_bounds) to N GPUs of the box -- one
-    process per GPU, no traffic while stepping -- gathers the rows on rank 0 and writes the same file."""
+    process per GPU, no traffic while stepping -- gathers the rows on rank 0 and writes the same file;
+    ``run(gpu_ids=[...])`` keeps one process and drives the GPUs through a fleet (kmos_b200_fleet_*)."""
 
     def __init__(self, model, size=20, seeds=1, parameters=None, device=0, name=None, model_factory=None):
         self.model_path, self.size, self.seeds, self.device = model, size, int(seeds), device
@@ -128,7 +134,7 @@ class ModelRunner(object):
         grids = [p.get_grid() for p in self.parameters.values()]
         return [dict(zip(self.parameters.keys(), (float(v) for v in pt))) for pt in itertools.product(*grids)]
 
-    def _gather(self, points, gpus, args):
+    def _gather(self, points, gpus, args, gpu_ids=None):
         """-> (header, rows of every grid point in grid order, parameter dump), or None on ranks > 0."""
         from . import parallel
         try:
@@ -146,6 +152,9 @@ class ModelRunner(object):
             dist.gather_object(mine, parts, dst=0)
             if rank != 0:
                 return None
+        elif gpu_ids is not None:  # this process drives the listed GPUs itself (kmos_b200_fleet_*)
+            parts = [_run_points(self.model_path, self.size, self.seeds, points, 0, self.device, *args,
+                                 model_factory=self.model_factory, gpu_ids=gpu_ids)]
         elif gpus and gpus > 1:  # one worker process per GPU of this box
             import multiprocessing as mp
             ctx = mp.get_context("spawn")
@@ -174,13 +183,14 @@ class ModelRunner(object):
         return parts[0][0], np.vstack([p[1] for p in parts]), parts[0][2]
 
     def run(self, init_steps=1e5, sample_steps=1e5, samples=1, random_seed=1, outfile=None, per_replica=False,
-            gpus=None):
+            gpus=None, gpu_ids=None):
         """Returns (header, rows).  One row per grid point (mean over its seeds) unless ``per_replica``.
         gpus: number of GPUs of this box to deal the grid points to (default: one, ``device``); under
-        torch.distributed.run the ranks of the job are used instead and only rank 0 returns rows."""
+        torch.distributed.run the ranks of the job are used instead and only rank 0 returns rows.
+        gpu_ids: run the scan as one fleet on these GPUs from this process, no workers (same rows again)."""
         points = self.grid_points()
         outfile = outfile or os.path.abspath("%s.dat" % self.runner_name)
-        got = self._gather(points, gpus, (init_steps, sample_steps, samples, random_seed))
+        got = self._gather(points, gpus, (init_steps, sample_steps, samples, random_seed), gpu_ids)
         if got is None:
             return None, None
         header, rows, params_dump = got

@@ -4,8 +4,12 @@ import numpy as np
 
 
 class FakeModel(object):
-    def __init__(self, model, size=20, n_replicas=1, parameters=None, device=0, seeds=None, replica_ids=None):
+    def __init__(self, model, size=20, n_replicas=1, parameters=None, device=0, seeds=None, replica_ids=None,
+                 gpu_ids=None):
         self.params, self.seeds, self.device = parameters, np.asarray(seeds, dtype=np.uint64), device
+        if gpu_ids is not None:  # a fleet numbers its replicas 0..R-1 itself
+            assert replica_ids is None and len(gpu_ids) > 0
+            replica_ids = np.arange(n_replicas)
         assert np.array_equal(np.asarray(replica_ids, dtype=np.uint64) + np.uint64(7), self.seeds)  # global ids
         self.steps = 0
 

@@ -127,3 +127,23 @@ def test_kmc_model_on_a_fleet_gives_the_single_gpu_rows(tmp_path):
         many.batch.reload_system(str(tmp_path / "r.reload"), replica=2)
         many.do_steps(700)
         assert np.array_equal(many.batch.lattice[2], ref)
+
+
+def test_model_runner_on_a_fleet_writes_the_same_dat_file(tmp_path):
+    """ModelRunner.run(gpu_ids=[...]): the scan as one fleet of this process -- byte for byte the .dat file of the
+    single-GPU scan (kmos/run/__init__.py:2129-2139 format)."""
+    import os
+    from conftest import GOLDEN
+    from kmos_b200 import runner
+
+    class Scan(runner.ModelRunner):
+        T = runner.TemperatureParameter(min=500, max=600, steps=3)
+        p_COgas = runner.PressureParameter(min=0.5, max=5, steps=3)
+
+    model = os.path.join(GOLDEN, "models", "ruo2_local_smart.json")
+    n_dev = capi.lib().kmos_b200_device_count()
+    kw = dict(init_steps=3000, sample_steps=3000, samples=2, random_seed=11)
+    h1, r1 = Scan(model, size=8, seeds=3, name="a").run(outfile=str(tmp_path / "a.dat"), **kw)
+    h2, r2 = Scan(model, size=8, seeds=3, name="b").run(outfile=str(tmp_path / "b.dat"), gpu_ids=[0, 1 % n_dev, 0, 0], **kw)
+    assert h1 == h2 and np.array_equal(r1, r2)
+    assert open(tmp_path / "a.dat").read() == open(tmp_path / "b.dat").read()

@@ -34,6 +34,10 @@ def test_run_on_several_gpus_gathers_the_same_rows(tmp_path):
     assert np.array_equal(rows1[:, 2], (7 + np.arange(30)) * 1e-3)
     a, b = open(tmp_path / "one.dat").read(), open(tmp_path / "three.dat").read()
     assert a == b and a.startswith("#T p_COgas tof kmc_steps\n# T = ") and len(a.splitlines()) == 1 + 2 + 2 + 30
+    # one process, the GPUs driven through a fleet: the same rows and file again
+    fleet = Scan("m.json", seeds=2, model_factory=fake_model.FakeModel, name="fleet")
+    hf, rowsf = fleet.run(outfile=str(tmp_path / "fleet.dat"), per_replica=True, gpu_ids=[0, 1, 2], **kw)
+    assert hf == h1 and np.array_equal(rowsf, rows1) and open(tmp_path / "fleet.dat").read() == a
     # means over the seeds of a grid point
     _h, rows = Scan("m.json", seeds=2, model_factory=fake_model.FakeModel).run(
         outfile=str(tmp_path / "mean.dat"), gpus=2, **kw)
