@@ -89,3 +89,18 @@ def test_fortran_interface_block_matches_the_header():
         n_c = 0 if m.group(1).strip() in ("", "void") else m.group(1).count(",") + 1
         n_f = len([a for a in fargs.replace("&", "").split(",") if a.strip()])
         assert n_c == n_f, (cname, n_c, n_f)
+
+
+def test_fleet_create_validates_its_arguments_before_touching_cuda(built):
+    """SURVEY 8b gpu_ids[]: an empty device list or no replicas is an argument error (-1) with or without a GPU."""
+    L = capi.lib()
+    ir, blob, info = load_model("mini_101_local_smart")
+    m, f = ctypes.c_void_p(), ctypes.c_void_p()
+    assert L.kmos_b200_model_create(blob, blob.size, ctypes.byref(m)) == 0
+    size = np.array([4, 4, 1], dtype=np.int32)
+    ids = np.array([0], dtype=np.int32)
+    assert L.kmos_b200_fleet_create(m, 4, size, None, ids, 0, ctypes.byref(f)) == -1
+    assert L.kmos_b200_fleet_create(m, 0, size, None, ids, 1, ctypes.byref(f)) == -1
+    assert b"fleet_create" in L.kmos_b200_last_error()
+    L.kmos_b200_fleet_destroy(None)  # a no-op, like free(NULL)
+    L.kmos_b200_model_destroy(m)
