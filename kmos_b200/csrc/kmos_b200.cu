@@ -263,23 +263,58 @@ __global__ void kb_occupation_kernel(const uint8_t* lattice, int lat_stride, int
 
 // tallies per group: [P] procstat | [P] integ | [ns*spuck] occupation | kmc_time | kmc_steps | n_replicas
 // One block per group; thread w owns word w and adds the group's replicas in replica order (deterministic).
-__global__ void kb_tally_kernel(const KbScalars* sc, const int64_t* procstat, const double* integ, const double* occ,
-                                const int32_t* group_of, int R, int P, int nocc, double* out, int words) {
-    const int grp = blockIdx.x;
-    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+// The group's members are first gathered, tile by tile and in replica order, into shared memory (ballot + rank
+// over the block), so a thread walks its group's replicas only, not all R group ids: 16 384 replicas in 256
+// groups took 0.87 ms per launch (2.7 % of a bench step) with every thread scanning group_of[] itself.
+#define KB_TALLY_THREADS 128
+#define KB_TALLY_TILE 2048
+__global__ void __launch_bounds__(KB_TALLY_THREADS) kb_tally_kernel(const KbScalars* sc, const int64_t* procstat, const double* integ,
+                                                                    const double* occ, const int32_t* group_of, int R, int P, int nocc,
+                                                                    double* out, int words) {
+    __shared__ int member[KB_TALLY_TILE];
+    __shared__ int wcount[KB_TALLY_THREADS / 32];
+    const int grp = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int w0 = 0; w0 < words; w0 += KB_TALLY_THREADS) {  // uniform trip count: the block synchronises inside
+        const int w = w0 + threadIdx.x;
         double acc = 0.0;
-        for (int rep = 0; rep < R; ++rep) {
-            if ((group_of ? group_of[rep] : 0) != grp) continue;
-            double v;
-            if (w < P) v = (double)procstat[(size_t)rep * P + w];
-            else if (w < 2 * P) v = integ[(size_t)rep * P + (w - P)];
-            else if (w < 2 * P + nocc) v = occ[(size_t)rep * nocc + (w - 2 * P)];
-            else if (w == 2 * P + nocc) v = sc[rep].kmc_time;
-            else if (w == 2 * P + nocc + 1) v = (double)sc[rep].kmc_step;
-            else v = 1.0;
-            acc += v;
+        for (int t0 = 0; t0 < R; t0 += KB_TALLY_TILE) {
+            const int t1 = min(R, t0 + KB_TALLY_TILE);
+            int n_mem = 0;
+            if (group_of) {
+                for (int base = t0; base < t1; base += KB_TALLY_THREADS) {
+                    const int rep = base + threadIdx.x;
+                    const bool m = rep < t1 && group_of[rep] == grp;
+                    const unsigned bal = __ballot_sync(0xffffffffu, m);
+                    if (lane == 0) wcount[warp] = __popc(bal);
+                    __syncthreads();
+                    int before = 0, all = 0;
+                    for (int k = 0; k < KB_TALLY_THREADS / 32; ++k) {
+                        before += k < warp ? wcount[k] : 0;
+                        all += wcount[k];
+                    }
+                    if (m) member[n_mem + before + __popc(bal & ((1u << lane) - 1u))] = rep;
+                    n_mem += all;
+                    __syncthreads();
+                }
+            } else {
+                n_mem = grp == 0 ? t1 - t0 : 0;  // no group ids: every replica belongs to group 0, no list needed
+            }
+            if (w < words) {
+                for (int i = 0; i < n_mem; ++i) {
+                    const int rep = group_of ? member[i] : t0 + i;
+                    double v;
+                    if (w < P) v = (double)procstat[(size_t)rep * P + w];
+                    else if (w < 2 * P) v = integ[(size_t)rep * P + (w - P)];
+                    else if (w < 2 * P + nocc) v = occ[(size_t)rep * nocc + (w - 2 * P)];
+                    else if (w == 2 * P + nocc) v = sc[rep].kmc_time;
+                    else if (w == 2 * P + nocc + 1) v = (double)sc[rep].kmc_step;
+                    else v = 1.0;
+                    acc += v;
+                }
+            }
+            __syncthreads();  // the list is rewritten by the next tile
         }
-        out[(size_t)grp * words + w] = acc;
+        if (w < words) out[(size_t)grp * words + w] = acc;
     }
 }
 
@@ -1389,7 +1424,7 @@ extern "C" int kmos_b200_reduce_tallies(kmos_b200_batch* b, const int32_t* group
     }
     int rc = compute_occupation(b, occ);
     if (rc) return rc;
-    kb_tally_kernel<<<n_groups, 128, 0, b->stream>>>(b->sc, b->procstat, b->integ, occ,
+    kb_tally_kernel<<<n_groups, KB_TALLY_THREADS, 0, b->stream>>>(b->sc, b->procstat, b->integ, occ,
                                                             group_of ? b->group_of : nullptr, b->R, m.n_proc, nocc, out, words);
     CU(cudaGetLastError());
     if (host_out) {  // asynchronous for callers that consume the device buffer (NCCL) themselves

@@ -67,3 +67,40 @@ def test_kernel_selection_and_fallback_reasons():
     b.do_steps(50)
     assert np.all(b.kmc_step == 50)
     b.close()
+
+
+@pytest.mark.parametrize("name,size,R", [
+    ("mini_101_local_smart", [5, 5], 5000),       # more replicas than one member tile (2048) of the tally kernel
+    ("pairwise84_local_smart", [8, 8], 300),      # 2 P + ... > 128 words: more than one word per thread
+])
+def test_tallies_are_ordered_group_sums(name, size, R):
+    """kb_tally_kernel: per-group sums over interleaved groups, added in replica order (so they are reproducible
+    bit for bit on the host), an empty group, and the ungrouped call."""
+    from kmos_b200 import engine
+    from util import make_inputs
+    ir, blob, info = load_model(name)
+    m = engine.Model(ir=ir, blob=blob, info=info)
+    rates, lut, seeds = make_inputs(ir, info, R, seed=5)
+    b = engine.Batch(m, R, size, seeds=seeds, rates=rates)
+    b.do_steps(200)
+    groups = (np.arange(R) * 7 % 5).astype(np.int32)   # five interleaved groups, a sixth stays empty
+    t = b.split_tally(b.reduce_tallies(groups, 6))
+    ps, integ, occ, time, steps = b.procstat, b.integ_rates, b.occupation.reshape(R, -1), b.kmc_time, b.kmc_step
+
+    def ordered(values, members):
+        acc = np.zeros(values.shape[1:])
+        for r in members:
+            acc = acc + values[r]
+        return acc
+    for g in range(6):
+        members = np.nonzero(groups == g)[0]
+        assert t["n_replicas"][g] == len(members) and t["kmc_steps"][g] == steps[members].sum()
+        assert np.array_equal(t["procstat"][g], ps[members].sum(axis=0))
+        assert np.array_equal(t["integ_rates"][g], ordered(integ, members))
+        assert np.array_equal(t["occupation"][g], ordered(occ, members))
+        assert t["kmc_time"][g] == ordered(time[:, None], members)[0]
+    assert t["n_replicas"][5] == 0 and not t["procstat"][5].any()
+    one = b.split_tally(b.reduce_tallies())
+    assert one["n_replicas"][0] == R and np.array_equal(one["procstat"][0], ps.sum(axis=0))
+    assert one["kmc_time"][0] == ordered(time[:, None], range(R))[0]
+    b.close()
